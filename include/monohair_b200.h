@@ -1,0 +1,191 @@
+/*
+ * monohair_b200 — C ABI of the B200-native MonoHair hot path (Gabor bank, PMVO, HairGrow trace).
+ *
+ * The reference (KeyuWu-CS/MonoHair) has no FFI: its boundary is Python.  This header is the
+ * contract the thin Python host (monohair_b200/*.py, mirroring PMVO.py / HairGrow.py / GaborFilter.py) binds
+ * with ctypes; each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a caller-allocated DEVICE pointer unless its name ends in _host;
+ *   - the library never allocates or frees; scratch comes from a caller workspace sized by *_workspace_bytes;
+ *   - sizes are int64_t, `stream` is a cudaStream_t passed as void*;
+ *   - no host synchronisation inside (except functions documented as synchronous);
+ *   - return 0 on success, non-zero on error; the message is mh_last_error() (thread-local).
+ *   - float32 everywhere unless noted; arithmetic follows the reference's fp32 operation order.
+ */
+#ifndef MONOHAIR_B200_H
+#define MONOHAIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MH_CAM_STRIDE 32   /* floats per view in mh_views.cam, see mh_views_pack_camera_host */
+#define MH_TOPK 20         /* PMVO.py:341 */
+#define MH_NUM_BASE 10     /* PMVO.py:50  range(0,20,2) */
+
+/* Resident per-view maps (PMVO.__init__, PMVO.py:14-37).  All device pointers, owned by the caller. */
+typedef struct mh_views {
+    int32_t V, H, W, P;        /* views, image rows, cols, patch size (odd) */
+    const void* mapC;          /* float2 [V][H][W] = {depth, mask'}   mask' = mask>0.2 ? 1 : mask  (PMVO.py:427) */
+    const void* mapP;          /* float4 [V][H][W] = {ori_row, ori_col, conf, max_{PxP} conf}      (PMVO.py:491-515) */
+    const float* cam;          /* [V][MH_CAM_STRIDE] */
+} mh_views;
+
+const char* mh_last_error(void);
+int mh_version(void);
+
+/* ---- views ------------------------------------------------------------------------------------------- */
+/* Fill cam[v] from host data: pose = world->camera 4x4 row-major (Camera.pose), ndc_prj = {fx,fy,cx,cy}
+ * (Camera.get_projection_matrix, Camera_utils.py:19-36), rinv = torch.linalg.inv(pose[:3,:3]) row-major
+ * (Camera_utils.py:104).  Host-side helper, writes 32 floats into cam_host. */
+int mh_views_pack_camera_host(const float* pose_host, const float* ndc_prj_host, const float* rinv_host,
+                              float* cam_host);
+
+/* Pack one view's float32 maps (already on the device) into mapC/mapP planes of view v.
+ * depth/mask: pixel stride in floats (3 for the reference's [H,W,3] arrays, channel 0 is read; PMVO.py:485,523).
+ * Replaces the per-view tensors kept by PMVO.__init__ (PMVO.py:23-26) and precomputes the PxP confidence
+ * maximum used by filter_points (PMVO.py:415-418) and compute_prj_loss (PMVO.py:162). */
+int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,
+                  const float* depth, int32_t depth_stride, const float* ori /*[H][W][2]*/,
+                  const float* conf /*[H][W]*/, const float* mask, int32_t mask_stride,
+                  void* mapC /*[V][H][W] float2*/, void* mapP /*[V][H][W] float4*/);
+
+/* Same from the on-disk 8-bit formats (best_ori gray, conf, mask) with the decode of
+ * Load_Ori_And_Conf / load_mask (PMVO_utils.py:255-313) fused; lut = 256x2 floats {sin o, cos o} built on host. */
+int mh_views_pack_u8(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,
+                     const float* depth, int32_t depth_stride, const uint8_t* ori_gray, const uint8_t* conf_u8,
+                     const uint8_t* mask_u8, const float* ori_lut /*[256][2]*/, const float* conf_lut /*[256]*/,
+                     const float* mask_lut /*[256]*/, void* mapC, void* mapP);
+
+/* ---- PMVO.filter_points (PMVO.py:402-459) ------------------------------------------------------------- */
+/* counters [5][N] = {sum vis, sum vis*mask, sum vis*low_conf, sum vis1, sum vis1*mask} over the views of
+ * `views` (a rank's shard when view-sharded; all-reduce(SUM) them across ranks). */
+int mh_filter_count(void* stream, const mh_views* views, const float* points /*[N][3]*/, int64_t N,
+                    float visible_threshold, float conf_threshold, float* counters /*[5][N]*/);
+/* surface / filter flags from (all-reduced) counters (PMVO.py:442-454). */
+int mh_filter_decide(void* stream, const float* counters, int64_t N, uint8_t* surface, uint8_t* filter);
+
+/* PMVO.compute_unvisible_points (PMVO.py:461-480): count [N] of views with dz<=0.9 and in image;
+ * unvisible = !(count > 2) is taken on the host side after the optional all-reduce. */
+int mh_visible_count(void* stream, const mh_views* views, const float* points, int64_t N, float dz_threshold,
+                     float* count /*[N]*/);
+
+/* PMVO.filter_head_points per-view part (PMVO.py:110-136): counters [2][N] = {sum vis, sum vis*mask'} with
+ * unvisible = dz >= visible_threshold (no out-of-image test, as in the reference). */
+int mh_head_count(void* stream, const mh_views* views, const float* points, int64_t N, float visible_threshold,
+                  float* counters /*[2][N]*/);
+
+/* filter = !(sum_vis - sum_vis*mask' < sum_vis/2) && !head_top, head_top = scalp_dist < dist_threshold (0.04)
+ * && point.z < z_threshold (scalp_max.z - 0.01), compared in float64 like the reference's numpy (PMVO.py:105-141). */
+int mh_head_decide(void* stream, const float* counters /*[2][N]*/, const double* scalp_dist /*[N]*/,
+                   const float* points, int64_t N, double dist_threshold, double z_threshold, uint8_t* filter);
+
+/* PMVO.Compute_Visible_and_Ori centre values (PMVO.py:346-376): visible [V][N], ori [V][N][2], conf [V][N]
+ * (clamped to [1e-6,1]), optional mask' [V][N] and rowcol int32 [V][N][2] (col stored as -col-1 when the
+ * projection fell outside the image: the unvisible_index of project_points, PMVO.py:384-395). */
+int mh_centre_gather(void* stream, const mh_views* views, const float* points, int64_t N, float* visible,
+                     float* ori, float* conf, float* mask, int32_t* rowcol);
+
+/* ---- PMVO.forward (PMVO.py:39-78) --------------------------------------------------------------------- */
+int64_t mh_pmvo_optimize_workspace_bytes(const mh_views* views, int64_t N);
+/* offsets: the S depth offsets of sample_next_3d_pos (PMVO.py:274-278), computed by the host with torch.arange.
+ * Outputs: ori [N][3] unit direction, loss [N], high_conf [N] (0/1).
+ * Optional debug outputs (may be NULL): base_idx int32 [MH_TOPK][N], base_val [MH_TOPK][N] (topk order of
+ * torch.topk on CPU), best_sample [N][3], loss_b [MH_NUM_BASE][N], arg_b int32 [MH_NUM_BASE][N]. */
+int mh_pmvo_optimize(void* stream, const mh_views* views, const float* points, int64_t N,
+                     const float* offsets, int32_t S, float conf_threshold,
+                     float* ori, float* loss, uint8_t* high_conf,
+                     int32_t* dbg_base_idx, float* dbg_base_val, float* dbg_best_sample,
+                     float* dbg_loss_b, int32_t* dbg_arg_b,
+                     void* workspace, int64_t workspace_bytes);
+
+/* PMVO.refine loss part (PMVO.py:82,86-90): single-sample reprojection loss for next = p + dir*0.00125.
+ * The head filter (loss[filter]=-1, PMVO.py:92) is applied by the caller from mh_head_count + scalp distance. */
+int mh_pmvo_refine_loss(void* stream, const mh_views* views, const float* points, const float* dir, int64_t N,
+                        float conf_threshold, float* loss);
+
+/* ---- kNN + medoid (PMVO.py:605-641, 660-686; PMVO_utils.py:366-382) ----------------------------------- */
+int64_t mh_knn_workspace_bytes(int64_t n_ref, int64_t n_query, int32_t k);
+/* Exact k nearest neighbours (Euclidean, float64 distances like scipy.spatial.KDTree on float64 data), sorted by
+ * (distance, index).  ref/query are float32 xyz.  idx int32 [n_query][k]. */
+int mh_knn(void* stream, const float* ref, int64_t n_ref, const float* query, int64_t n_query, int32_t k,
+           const double* bbox_host /*{min xyz, max xyz} of ref*/, double cell_size,
+           int32_t* idx, void* workspace, int64_t workspace_bytes);
+/* Nearest-reference distance only (k=1), float64 [n_query]: scalp_tree.query(points,k=1) (PMVO.py:104). */
+int mh_nn_dist(void* stream, const double* ref, int64_t n_ref, const float* query, int64_t n_query, double* dist);
+/* medoid of ori[nbr[i][0..K)] under |cos| (compute_points_similarity): out [n][3], out_k int32 [n] (may be NULL). */
+int mh_medoid_gather(void* stream, const float* ori /*[n_ref][3]*/, const int32_t* nbr /*[n][K]*/, int64_t n,
+                     int32_t K, float* out, int32_t* out_k);
+
+/* In-place chunk update of PMVO.refine step (i) (PMVO.py:629-641): loss = head_filter ? 0.5 : upd_loss
+ * (the -1 marker of PMVO.py:92 becomes 0.5 at :639); ori = center where |cos(center, ori)| < 0.95. */
+int mh_refine_update(void* stream, const float* center, const float* upd_loss, const uint8_t* head_filter,
+                     int64_t n, float* ori /*in/out [n][3]*/, float* loss /*out [n]*/);
+
+/* ---- voxel fusion (PMVO.py:695-726, PMVO_utils.p2v :386-404) ------------------------------------------ */
+int64_t mh_voxel_fuse_workspace_bytes(int64_t n_points, int32_t gx, int32_t gy, int32_t gz);
+/* points float32 [n][3] (world), dirs float32 [n][3].  Flips dirs to dir.y<=0 (PMVO.py:702-703), voxelises with
+ * float64 index math (np.round half-even), takes the per-voxel medoid in original point order and writes the
+ * fused volume as float4 [gz][gy][gx] = {ori.x, -ori.y, -ori.z, occ}: the layout/sign HairGrowing.__init__
+ * builds from the .mat pair (HairGrow.py:45-55).  vox_index int32 [n] (linear id x*gy*gz+y*gz+z; may be NULL). */
+int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
+                  const double* voxel_min_host /*[3]*/, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
+                  void* volume /*float4 [gz][gy][gx]*/, int32_t* vox_index, void* workspace, int64_t workspace_bytes);
+/* Overwrite voxels with given orientations, last writer wins (raw.npy merge, PMVO.py:747-749). */
+int mh_voxel_overwrite(void* stream, const float* points, const float* dirs, int64_t n,
+                       const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
+                       void* volume, void* winner_ws /* int32 [gz*gy*gx] scratch */);
+/* float4 volume -> the float64 arrays scipy.io.savemat receives (PMVO.py:753-756):
+ * Occ [gy][gx][gz], Ori [gy][gx][3*gz] (index c*gz+z), world-frame signs. */
+int mh_volume_to_mat(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, double* occ, double* ori);
+/* and back (get_ground_truth_3D_occ/ori + HairGrowing.__init__, PMVO_utils.py:86-113, HairGrow.py:45-55). */
+int mh_volume_from_mat(void* stream, const double* occ, const double* ori, int32_t gx, int32_t gy, int32_t gz,
+                       void* volume);
+
+/* ---- HairGrow trace (HairGrow.py:59-299) -------------------------------------------------------------- */
+/* Pass 1: lengths.  seeds float32 [n][3] are the jittered seed positions (seed + 0.5 + U[0,0.5)^3 applied by the
+ * caller so RNG draws can be injected).  n_fwd/n_bwd int32 [n]: accepted steps each way. */
+int mh_trace_count(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* seeds,
+                   int64_t n, float thr_dot, int32_t max_steps, int32_t* n_fwd, int32_t* n_bwd);
+/* Pass 2: write strands (backward part reversed, seed, forward part) at offsets[i] (in points) for strands with
+ * n_fwd+n_bwd+1 >= min_len; others are skipped.  points_out float32 [total][3] voxel coordinates. */
+int mh_trace_write(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* seeds,
+                   int64_t n, float thr_dot, int32_t max_steps, const int32_t* n_fwd, const int32_t* n_bwd,
+                   const int64_t* offsets, int32_t min_len, float* points_out);
+/* traceFromScalp (HairGrow.py:154-223): one pass, fixed-stride output [n][max_steps+1][3]; length int32 [n]
+ * (0 when the reference returns None). */
+int mh_trace_from_scalp(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* roots,
+                        const float* normals, int64_t n, float thr_dot, int32_t max_steps, int32_t max_inner,
+                        float* points_out, int32_t* length);
+/* Ordered acceptance (GenerateGuideStrandFromScalp / randomlyGenerateSegments flag logic, HairGrow.py:235-260,
+ * 280-293): strands in order; reject when flag[seed voxel] >= 3, else accept and bump flag once per unique voxel
+ * (mode 0: += 1; mode 1: = 1 and no gating, the scalp pass).  flag float32 [gz][gy][gx].  accepted uint8 [n]. */
+int mh_accept_strands(void* stream, const float* points, const int64_t* offsets, const int32_t* lengths,
+                      const float* seeds, int64_t n, int32_t gx, int32_t gy, int32_t gz, int32_t mode,
+                      float* flag, uint8_t* accepted);
+
+/* ---- Gabor bank (GaborFilter.py:29-145, calc_orientation_maps.py:18-49) ------------------------------- */
+/* calOrientationGabor.filter+forward for iter=1: image [H][W] -> orient [H][W] (radians), conf [H][W],
+int64_t mh_gabor_workspace_bytes(int32_t H, int32_t W, int32_t n_filters);
+int mh_gabor_orientation(void* stream, const float* image, int32_t H, int32_t W, const float* bank, int32_t n_filters,
+                         int32_t ksize, float clamp_low, float clamp_high, float* orient, float* conf,
+                         float* two_channel, void* workspace, int64_t workspace_bytes);
+/* Generic filter-bank responses in float64 with periodic ('wrap') true convolution: calc_orients
+ * (calc_orientation_maps.py:27-32).  bank [n][k][k] zero-padded to k x k; out |response| [n][H][W]. */
+int mh_filterbank_wrap_f64(void* stream, const double* image, int32_t H, int32_t W, const double* bank,
+                           int32_t n_filters, int32_t ksize, double* out_abs);
+/* Separable Gaussian (scipy.ndimage.gaussian_filter, mode='nearest') difference: difference_of_gaussians. */
+int mh_dog_f64(void* stream, const double* image, int32_t H, int32_t W, const double* k_lo, int32_t r_lo,
+               const double* k_hi, int32_t r_hi, double* out, double* scratch /*[2][H][W]*/);
+
+/* ---- host-side test hooks (no GPU needed): the same __host__ __device__ code the kernels run ---------- */
+/* order of torch.topk(k=20, dim=0, largest, sorted) on CPU for one column of V values (PMVO.py:341). */
+int mh_debug_topk_host(const float* values_host, int32_t V, int32_t k, int32_t* idx_host, float* val_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,469 @@
+// Refine stage kernels (PMVO.refine module function, PMVO.py:602-686):
+//   mh_pmvo_refine_loss   PMVO.refine's single-sample reprojection loss (PMVO.py:81-93)
+//   mh_knn                scipy.spatial.KDTree.query(k) replacement: exact kNN on a uniform grid
+//   mh_nn_dist            scalp_tree.query(points, k=1) distance (PMVO.py:104)
+//   mh_medoid_gather      compute_points_similarity on gathered neighbours (PMVO_utils.py:366-382)
+#include "mh_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ refine loss
+// One warp per point, lanes over views.  With a single sample "low_conf_index" is always true
+// (sum over 1 sample < 5, PMVO.py:199) so the result is sum(l*w)/sum(w) over the views, cascade order.
+constexpr int RL_WARPS = 8;
+
+__global__ void __launch_bounds__(RL_WARPS * 32)
+refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __restrict__ dir, int64_t N,
+                   float thr_c, float* __restrict__ out_loss) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MhCam* cams = reinterpret_cast<MhCam*>(smem_raw);
+    float* lw = reinterpret_cast<float*>(cams + vw.V);          // [RL_WARPS][V][2]
+    const int V = vw.V, P = vw.P, half = P / 2, PP = P * P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < V * MH_CAM_STRIDE; i += blockDim.x) reinterpret_cast<float*>(cams)[i] = vw.cam[i];
+    __syncthreads();
+    float* my = lw + (size_t)warp * V * 2;
+    const float Wf = (float)vw.W, Hf = (float)vw.H;
+    const float2* __restrict__ mapC = reinterpret_cast<const float2*>(vw.mapC);
+    const float4* __restrict__ mapP = reinterpret_cast<const float4*>(vw.mapP);
+    const size_t plane = (size_t)vw.H * vw.W;
+    for (int64_t n = (int64_t)blockIdx.x * RL_WARPS + warp; n < N; n += (int64_t)gridDim.x * RL_WARPS) {
+        const float px = pts[3 * n], py = pts[3 * n + 1], pz = pts[3 * n + 2];
+        // next = p + ori * 0.005 / 4   (PMVO.py:86)
+        const float qx = px + dir[3 * n] * 0.005f / 4.0f, qy = py + dir[3 * n + 1] * 0.005f / 4.0f,
+                    qz = pz + dir[3 * n + 2] * 0.005f / 4.0f;
+        for (int v = lane; v < V; v += 32) {
+            const MhCam& cm = cams[v];
+            float cx, cy, cz, xp, yp, xs, ys;
+            mh_world_to_cam(cm.p, px, py, pz, cx, cy, cz);
+            mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, cx, cy, cz, xp, yp);
+            int row, col; bool oob;
+            mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
+            const size_t base = (size_t)v * plane;
+            const float2 dm = __ldg(mapC + base + (size_t)row * vw.W + col);
+            float vis = mh_visible((-cz / 2.0f) * 255.0f, dm.x);
+            if (oob) vis = -1.0f;
+            float l_w = 0.0f, w = 0.0f;
+            if (vis != -1.0f) {
+                float c2x, c2y, c2z;
+                mh_world_to_cam(cm.p, qx, qy, qz, c2x, c2y, c2z);
+                mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, c2x, c2y, c2z, xs, ys);
+                float y0, y1;
+                mh_normalize2(ys - yp, xs - xp, y0, y1);
+                const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mapP + base + (size_t)row * vw.W + col) + 3), 1e-6f), 1.0f);
+                const bool hi = cmax > thr_c;
+                float bl = 0.0f, bc = 0.0f;
+                for (int p = 0; p < PP; ++p) {
+                    const int di = p / P - half, dj = p % P - half;
+                    const int r = min(max(row + di, 0), vw.H - 1), c = min(max(col + dj, 0), vw.W - 1);
+                    const float4 t = __ldg(mapP + base + (size_t)r * vw.W + c);
+                    float x0, x1;
+                    mh_normalize2(t.x, t.y, x0, x1);
+                    const float cf = fminf(fmaxf(t.z, 1e-6f), 1.0f);
+                    const float l = 1.0f - fabsf(x0 * y0 + x1 * y1);
+                    if (p == 0) { bl = l; bc = cf; }
+                    else if (l < bl && (!hi || cf > thr_c)) { bl = l; bc = cf; }
+                }
+                w = bc;
+                l_w = bl * bc;
+            }
+            my[2 * v] = l_w;
+            my[2 * v + 1] = w;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            MhCascade<2> acc;
+            acc.init(V);
+            for (int v = 0; v < V; ++v) {
+                if (my[2 * v + 1] == 0.0f && my[2 * v] == 0.0f) continue;
+                acc.begin_row(v);
+                acc.add(0, my[2 * v]);
+                acc.add(1, my[2 * v + 1]);
+            }
+            float s[2];
+            acc.finish(V, s);
+            out_loss[n] = s[0] / s[1];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ kNN grid
+struct Grid {
+    double ox, oy, oz, h;       // origin and cell size
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ int cell_of(double p, double o, double h, int n) {
+    int c = (int)floor((p - o) / h);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+__global__ void knn_count_kernel(Grid g, const float* __restrict__ ref, int64_t n, int* __restrict__ counts,
+                                 int* __restrict__ cell_of_pt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cx = cell_of(ref[3 * i], g.ox, g.h, g.nx), cy = cell_of(ref[3 * i + 1], g.oy, g.h, g.ny),
+        cz = cell_of(ref[3 * i + 2], g.oz, g.h, g.nz);
+    int c = (cz * g.ny + cy) * g.nx + cx;
+    cell_of_pt[i] = c;
+    atomicAdd(counts + c, 1);
+}
+
+__global__ void knn_fill_kernel(const int* __restrict__ cell_of_pt, int64_t n, const int* __restrict__ starts,
+                                int* __restrict__ cursor, int* __restrict__ items) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cell_of_pt[i];
+    items[starts[c] + atomicAdd(cursor + c, 1)] = (int)i;
+}
+
+// ---- single-CTA-per-tile exclusive scan (3 kernels) ----
+constexpr int SCAN_BLOCK = 1024, SCAN_ITEMS = 4;
+
+__global__ void scan_local_kernel(const int* __restrict__ in, int* __restrict__ out, int64_t n, int* __restrict__ block_sums) {
+    __shared__ int sh[SCAN_BLOCK];
+    const int64_t base = ((int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    int v[SCAN_ITEMS], tot = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; tot += v[k]; }
+    sh[threadIdx.x] = tot;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - tot;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = run; run += v[k]; }
+    if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void scan_sums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ total) {
+    // one CTA; sequential over chunks of blockDim
+    __shared__ int sh[SCAN_BLOCK];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += SCAN_BLOCK) {
+        int i = b0 + threadIdx.x;
+        int x = (i < nb) ? block_sums[i] : 0;
+        sh[threadIdx.x] = x;
+        __syncthreads();
+        for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+            int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nb) block_sums[i] = carry + sh[threadIdx.x] - x;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry += sh[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void scan_add_kernel(int* __restrict__ out, int64_t n, const int* __restrict__ block_sums) {
+    const int64_t base = ((int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    const int add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) out[base + k] += add;
+}
+
+}  // namespace
+
+// exclusive scan of n ints: out[i] = sum_{j<i} in[j]; out[n] = total.  scratch >= ceil(n/4096) ints.
+int mh_exclusive_scan(cudaStream_t st, const int* in, int* out, int64_t n, int* scratch) {
+    const int64_t per = (int64_t)SCAN_BLOCK * SCAN_ITEMS;
+    const int nb = (int)((n + per - 1) / per);
+    scan_local_kernel<<<nb, SCAN_BLOCK, 0, st>>>(in, out, n, scratch);
+    scan_sums_kernel<<<1, SCAN_BLOCK, 0, st>>>(scratch, nb, out + n);
+    scan_add_kernel<<<nb, SCAN_BLOCK, 0, st>>>(out, n, scratch);
+    return 0;
+}
+
+namespace {
+
+// ---- query: one warp per query, candidate buffer of 256 (dist2, idx) kept in shared memory ----
+constexpr int KNN_WARPS = 4, KNN_BUF = 256, KNN_MAXK = 128;
+
+struct Cand { double d; int i; int pad; };
+
+__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) { return a.d < b.d || (a.d == b.d && a.i < b.i); }
+
+// bitonic sort of 256 candidates by one warp (8 per lane)
+__device__ void warp_sort256(Cand* buf, int lane) {
+    for (int k = 2; k <= KNN_BUF; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < KNN_BUF / 2; t += 32) {
+                // element pair (i, i^j) with i having bit j clear
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int p = i | j;
+                bool up = (i & k) == 0;
+                Cand a = buf[i], b = buf[p];
+                if (cand_less(b, a) == up) { buf[i] = b; buf[p] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_query_kernel(Grid g, const float* __restrict__ ref, const int* __restrict__ starts, const int* __restrict__ items,
+                 const float* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx) {
+    __shared__ Cand bufs[KNN_WARPS][KNN_BUF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Cand* buf = bufs[warp];
+    const double INF = 1e300;
+    for (int64_t q = (int64_t)blockIdx.x * KNN_WARPS + warp; q < nq; q += (int64_t)gridDim.x * KNN_WARPS) {
+        const double qx = query[3 * q], qy = query[3 * q + 1], qz = query[3 * q + 2];
+        const int cx = cell_of(qx, g.ox, g.h, g.nx), cy = cell_of(qy, g.oy, g.h, g.ny), cz = cell_of(qz, g.oz, g.h, g.nz);
+        for (int t = lane; t < KNN_BUF; t += 32) { buf[t].d = INF; buf[t].i = 0x7fffffff; }
+        __syncwarp();
+        int npend = 0;                 // pending candidates live in buf[K .. K+npend)
+        double bound = INF;            // current k-th best distance
+        const int cap = KNN_BUF - K;
+        const int maxR = max(max(max(cx, g.nx - 1 - cx), max(cy, g.ny - 1 - cy)), max(cz, g.nz - 1 - cz));
+        for (int R = 0; R <= maxR; ++R) {
+            // cells on the Chebyshev shell of radius R, clipped to the grid
+            const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
+            const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+            const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    const bool edge_zy = (abs(z - cz) == R) || (abs(y - cy) == R);
+                    // on an edge row every x is on the shell (contiguous cells -> contiguous items);
+                    // otherwise only x = cx-R and cx+R.
+                    for (int seg = 0; seg < (edge_zy ? 1 : 2); ++seg) {
+                        int xa, xb;
+                        if (edge_zy) { xa = x0; xb = x1; }
+                        else {
+                            int xx = seg == 0 ? cx - R : cx + R;
+                            if (xx < 0 || xx >= g.nx || (seg == 1 && R == 0)) continue;
+                            xa = xb = xx;
+                        }
+                        const int rowc = (z * g.ny + y) * g.nx;
+                        const int s = starts[rowc + xa], e = starts[rowc + xb + 1];
+                        for (int it0 = s; it0 < e; it0 += 32) {
+                            const int it = it0 + lane;
+                            bool ok = false;
+                            Cand c; c.d = INF; c.i = 0; c.pad = 0;
+                            if (it < e) {
+                                const int ri = items[it];
+                                const double dx = qx - (double)ref[3 * ri], dy = qy - (double)ref[3 * ri + 1], dz = qz - (double)ref[3 * ri + 2];
+                                c.d = dx * dx + dy * dy + dz * dz;
+                                c.i = ri;
+                                ok = c.d <= bound;
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, ok);
+                            const int add = __popc(m);
+                            if (npend + add > cap) {
+                                warp_sort256(buf, lane);
+                                for (int t = K + lane; t < KNN_BUF; t += 32) { buf[t].d = INF; buf[t].i = 0x7fffffff; }
+                                __syncwarp();
+                                bound = buf[K - 1].d;
+                                npend = 0;
+                                ok = ok && c.d <= bound;
+                            }
+                            const unsigned m2 = __ballot_sync(0xffffffffu, ok);
+                            if (ok) buf[K + npend + __popc(m2 & ((1u << lane) - 1))] = c;
+                            npend += __popc(m2);
+                            __syncwarp();
+                        }
+                    }
+                }
+            // termination: every unvisited point lies outside the (2R+1)^3 block around the query cell
+            if (npend > 0) {
+                warp_sort256(buf, lane);
+                for (int t = K + lane; t < KNN_BUF; t += 32) { buf[t].d = INF; buf[t].i = 0x7fffffff; }
+                __syncwarp();
+                bound = buf[K - 1].d;
+                npend = 0;
+            }
+            double margin = INF;
+            if (cx - R > 0) margin = fmin(margin, qx - (g.ox + (double)(cx - R) * g.h));
+            if (cx + R < g.nx - 1) margin = fmin(margin, (g.ox + (double)(cx + R + 1) * g.h) - qx);
+            if (cy - R > 0) margin = fmin(margin, qy - (g.oy + (double)(cy - R) * g.h));
+            if (cy + R < g.ny - 1) margin = fmin(margin, (g.oy + (double)(cy + R + 1) * g.h) - qy);
+            if (cz - R > 0) margin = fmin(margin, qz - (g.oz + (double)(cz - R) * g.h));
+            if (cz + R < g.nz - 1) margin = fmin(margin, (g.oz + (double)(cz + R + 1) * g.h) - qz);
+            if (margin > 0 && bound < margin * margin) break;
+        }
+        for (int t = lane; t < K; t += 32) out_idx[q * K + t] = buf[t].i;
+        __syncwarp();
+    }
+}
+
+__global__ void nn_dist_kernel(const double* __restrict__ ref, int64_t nref, const float* __restrict__ query,
+                               int64_t nq, double* __restrict__ dist) {
+    // brute force, one thread per query, reference tiles through shared memory
+    __shared__ double tile[256 * 3];
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double qx = 0, qy = 0, qz = 0, best = 1e300;
+    if (q < nq) { qx = query[3 * q]; qy = query[3 * q + 1]; qz = query[3 * q + 2]; }
+    for (int64_t r0 = 0; r0 < nref; r0 += 256) {
+        const int nt = (int)min((int64_t)256, nref - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt * 3; i += blockDim.x) tile[i] = ref[3 * r0 + i];
+        __syncthreads();
+        for (int i = 0; i < nt; ++i) {
+            const double dx = qx - tile[3 * i], dy = qy - tile[3 * i + 1], dz = qz - tile[3 * i + 2];
+            best = fmin(best, dx * dx + dy * dy + dz * dz);
+        }
+    }
+    if (q < nq) dist[q] = sqrt(best);
+}
+
+// ------------------------------------------------------------------------------------------ medoid
+constexpr int MED_WARPS = 4;
+
+__global__ void __launch_bounds__(MED_WARPS * 32)
+medoid_gather_kernel(const float* __restrict__ ori, const int* __restrict__ nbr, int64_t n, int K,
+                     float* __restrict__ out, int* __restrict__ out_k) {
+    extern __shared__ float sh[];                       // [MED_WARPS][K][3] normalised + [K] raw index
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* u = sh + (size_t)warp * K * 3;
+    for (int64_t i = (int64_t)blockIdx.x * MED_WARPS + warp; i < n; i += (int64_t)gridDim.x * MED_WARPS) {
+        for (int k = lane; k < K; k += 32) {
+            const int r = nbr[i * K + k];
+            const float a = ori[3 * r], b = ori[3 * r + 1], c = ori[3 * r + 2];
+            const float nn = fmaxf(mh_norm3(a, b, c), 1e-8f);
+            u[3 * k] = a / nn; u[3 * k + 1] = b / nn; u[3 * k + 2] = c / nn;
+        }
+        __syncwarp();
+        float best = -1e30f; int bk = 0x7fffffff;
+        for (int k = lane; k < K; k += 32) {
+            const float a = u[3 * k], b = u[3 * k + 1], c = u[3 * k + 2];
+            float s = 0.0f;
+            for (int j = 0; j < K; ++j) s += fabsf((a * u[3 * j] + b * u[3 * j + 1]) + c * u[3 * j + 2]);
+            s = s / (float)K;
+            if (s > best) { best = s; bk = k; }        // ascending k: first maximum kept
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+        }
+        if (lane == 0) {
+            const int r = nbr[i * K + bk];
+            out[3 * i] = ori[3 * r]; out[3 * i + 1] = ori[3 * r + 1]; out[3 * i + 2] = ori[3 * r + 2];
+            if (out_k) out_k[i] = bk;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+extern "C" int mh_pmvo_refine_loss(void* stream, const mh_views* vw, const float* points, const float* dir,
+                                   int64_t N, float conf_threshold, float* loss) {
+    MH_CHECK_ARG(vw && vw->mapC && vw->mapP && vw->cam, "null views");
+    MH_CHECK_ARG(points && dir && loss && N >= 0, "bad arguments");
+    if (N == 0) return 0;
+    const size_t smem = sizeof(MhCam) * vw->V + sizeof(float) * 2 * vw->V * RL_WARPS;
+    MH_CHECK_ARG(smem <= 200 * 1024, "too many views");
+    cudaFuncSetAttribute(refine_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = (N + RL_WARPS - 1) / RL_WARPS;
+    const int64_t cap = (int64_t)mh_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    refine_loss_kernel<<<(unsigned)blocks, RL_WARPS * 32, smem, (cudaStream_t)stream>>>(*vw, points, dir, N, conf_threshold, loss);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+// workspace layout for kNN: [grid header 64 B][counts ncell+1][starts ncell+1][cursor ncell][cell_of_pt n][items n][scan scratch]
+static const int64_t KNN_MAX_CELLS = 1ll << 24;
+
+extern "C" int64_t mh_knn_workspace_bytes(int64_t n_ref, int64_t n_query, int32_t k) {
+    (void)n_query; (void)k;
+    return 256 + 4 * (3 * (KNN_MAX_CELLS + 2) + 2 * n_ref + KNN_MAX_CELLS / 4096 + 16);
+}
+
+extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float* query, int64_t n_query, int32_t k,
+                      const double* bbox_host, double cell_size, int32_t* idx, void* workspace, int64_t workspace_bytes) {
+    MH_CHECK_ARG(ref && query && idx && workspace && bbox_host, "null pointer");
+    MH_CHECK_ARG(k >= 1 && k <= KNN_MAXK && k <= n_ref, "k must be in [1,128] and <= n_ref");
+    MH_CHECK_ARG(workspace_bytes >= mh_knn_workspace_bytes(n_ref, n_query, k), "workspace too small");
+    MH_CHECK_ARG(cell_size > 0, "cell size must be > 0");
+    if (n_query == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    double hdr[7] = {bbox_host[0], bbox_host[1], bbox_host[2], bbox_host[3], bbox_host[4], bbox_host[5], cell_size};
+    Grid g;
+    g.h = hdr[6];
+    g.ox = hdr[0]; g.oy = hdr[1]; g.oz = hdr[2];
+    auto dim = [&](double lo, double hi) { double d = floor((hi - lo) / g.h) + 1; return (int)fmin(fmax(d, 1.0), 1024.0); };
+    g.nx = dim(hdr[0], hdr[3]); g.ny = dim(hdr[1], hdr[4]); g.nz = dim(hdr[2], hdr[5]);
+    while ((int64_t)g.nx * g.ny * g.nz > KNN_MAX_CELLS) {      // coarsen
+        g.h *= 1.26;
+        g.nx = dim(hdr[0], hdr[3]); g.ny = dim(hdr[1], hdr[4]); g.nz = dim(hdr[2], hdr[5]);
+    }
+    const int64_t ncell = (int64_t)g.nx * g.ny * g.nz;
+    int* base = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 256);
+    int* counts = base;
+    int* starts = counts + (KNN_MAX_CELLS + 2);
+    int* cursor = starts + (KNN_MAX_CELLS + 2);
+    int* cell_of_pt = cursor + (KNN_MAX_CELLS + 2);
+    int* items = cell_of_pt + n_ref;
+    int* scratch = items + n_ref;
+    cudaMemsetAsync(counts, 0, sizeof(int) * (ncell + 1), st);
+    cudaMemsetAsync(cursor, 0, sizeof(int) * ncell, st);
+    knn_count_kernel<<<(unsigned)((n_ref + 255) / 256), 256, 0, st>>>(g, ref, n_ref, counts, cell_of_pt);
+    mh_exclusive_scan(st, counts, starts, ncell, scratch);
+    knn_fill_kernel<<<(unsigned)((n_ref + 255) / 256), 256, 0, st>>>(cell_of_pt, n_ref, starts, cursor, items);
+    int64_t blocks = (n_query + KNN_WARPS - 1) / KNN_WARPS;
+    const int64_t cap = (int64_t)mh_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    knn_query_kernel<<<(unsigned)blocks, KNN_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_nn_dist(void* stream, const double* ref, int64_t n_ref, const float* query, int64_t n_query, double* dist) {
+    MH_CHECK_ARG(ref && query && dist && n_ref >= 1, "bad arguments");
+    if (n_query == 0) return 0;
+    nn_dist_kernel<<<(unsigned)((n_query + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ref, n_ref, query, n_query, dist);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_medoid_gather(void* stream, const float* ori, const int32_t* nbr, int64_t n, int32_t K,
+                                float* out, int32_t* out_k) {
+    MH_CHECK_ARG(ori && nbr && out && K >= 1 && K <= 1024, "bad arguments");
+    if (n == 0) return 0;
+    const size_t smem = sizeof(float) * 3 * K * MED_WARPS;
+    int64_t blocks = (n + MED_WARPS - 1) / MED_WARPS;
+    const int64_t cap = (int64_t)mh_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    medoid_gather_kernel<<<(unsigned)blocks, MED_WARPS * 32, smem, (cudaStream_t)stream>>>(ori, nbr, n, K, out, out_k);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- per-chunk in-place update of PMVO.refine step (i) (PMVO.py:629-641) ---------------------------------
+namespace {
+__global__ void refine_update_kernel(const float* __restrict__ center, const float* __restrict__ upd_loss,
+                                     const uint8_t* __restrict__ head_filter, int64_t n, float* __restrict__ ori,
+                                     float* __restrict__ loss) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float l = head_filter[i] ? -1.0f : upd_loss[i];              // PMVO.py:92
+    if (l == -1.0f) l = 0.5f;                                    // :639
+    loss[i] = l;
+    const float c0 = center[3 * i], c1 = center[3 * i + 1], c2 = center[3 * i + 2];
+    const float o0 = ori[3 * i], o1 = ori[3 * i + 1], o2 = ori[3 * i + 2];
+    const float nc = fmaxf(mh_norm3(c0, c1, c2), 1e-8f), no = fmaxf(mh_norm3(o0, o1, o2), 1e-8f);
+    const float sim = fabsf(((c0 / nc) * (o0 / no) + (c1 / nc) * (o1 / no)) + (c2 / nc) * (o2 / no));   // :631-633
+    if (sim < 0.95f) { ori[3 * i] = c0; ori[3 * i + 1] = c1; ori[3 * i + 2] = c2; }                       // :634-636
+}
+}  // namespace
+
+extern "C" int mh_refine_update(void* stream, const float* center, const float* upd_loss, const uint8_t* head_filter,
+                                int64_t n, float* ori, float* loss) {
+    MH_CHECK_ARG(center && upd_loss && head_filter && ori && loss && n >= 0, "bad arguments");
+    if (n == 0) return 0;
+    refine_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(center, upd_loss, head_filter, n, ori, loss);
+    MH_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,210 @@
+// HairGrow strand tracing through the fused volume (HairGrow.py:59-299).
+//
+// Volume: float4 [gz][gy][gx] = {ori.x, ori.y, ori.z, occ} in HairGrowing's frame (one 16 B fetch per step).
+// The reference trace is a NEAREST-voxel walk with unit steps (position += orientation), not a trilinear one
+// (SURVEY.md §9-R15).  Each walk is a chain of dependent fetches, so the kernels run one thread per
+// (seed, direction) and rely on many resident walks to cover the L2/HBM latency; strand geometry does not depend
+// on the `flag` volume (§9-R9), which is handled afterwards by the ordered acceptance pass mh_accept_strands.
+// Bound: memory latency / random 32 B sector rate, not streaming bandwidth.  Algorithmic bytes per step = 16.
+#include "mh_common.cuh"
+
+namespace {
+
+struct Vol { const float4* v; int gx, gy, gz; };
+
+// .type(torch.long) truncates toward zero, then clamp (HairGrow.py:66-69, §9-R10)
+__device__ __forceinline__ int vox_index(const Vol& g, float x, float y, float z) {
+    const int ix = min(max((int)x, 0), g.gx - 1), iy = min(max((int)y, 0), g.gy - 1), iz = min(max((int)z, 0), g.gz - 1);
+    return (iz * g.gy + iy) * g.gx + ix;
+}
+// torch.dot of 3-vectors on CPU: (a0*b0 + a1*b1) + a2*b2, products rounded separately (probe)
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return (a0 * b0 + a1 * b1) + a2 * b2;
+}
+
+// One direction of HairGrowing.trace (HairGrow.py:78-105 forward, :116-143 backward with sign=-1).
+// Emit(k, x,y,z) is called for the k-th accepted step (k = 0,1,...).  Returns the number of accepted steps.
+template <typename Emit>
+__device__ __forceinline__ int walk(const Vol& g, float px, float py, float pz, float sign, float thr, int max_steps, Emit emit) {
+    float4 cur = __ldg(g.v + vox_index(g, px, py, pz));
+    float tx = cur.x, ty = cur.y, tz = cur.z;
+    int count = 0;
+    for (;;) {
+        if (cur.w == 0.0f) break;                                   // occ of the current voxel
+        const float nx = px + sign * tx, ny = py + sign * ty, nz = pz + sign * tz;
+        const float4 nxt = __ldg(g.v + vox_index(g, nx, ny, nz));
+        if (dot3(nxt.x, nxt.y, nxt.z, tx, ty, tz) < thr) break;
+        px = nx; py = ny; pz = nz;
+        tx = nxt.x; ty = nxt.y; tz = nxt.z;
+        cur = nxt;
+        emit(count, px, py, pz);
+        if (++count >= max_steps) break;
+    }
+    return count;
+}
+
+__global__ void trace_count_kernel(Vol g, const float* __restrict__ seeds, int64_t n, float thr, int max_steps,
+                                   int* __restrict__ n_fwd, int* __restrict__ n_bwd) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    const int64_t i = t >> 1;
+    const bool bwd = t & 1;
+    const int c = walk(g, seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2], bwd ? -1.0f : 1.0f, thr, max_steps,
+                       [](int, float, float, float) {});
+    (bwd ? n_bwd : n_fwd)[i] = c;
+}
+
+__global__ void trace_write_kernel(Vol g, const float* __restrict__ seeds, int64_t n, float thr, int max_steps,
+                                   const int* __restrict__ n_fwd, const int* __restrict__ n_bwd,
+                                   const int64_t* __restrict__ offsets, int min_len, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    const int64_t i = t >> 1;
+    const bool bwd = t & 1;
+    const int nb = n_bwd[i], nf = n_fwd[i];
+    if (nb + nf + 1 < min_len) return;
+    float* base = out + 3 * offsets[i];
+    const float sx = seeds[3 * i], sy = seeds[3 * i + 1], sz = seeds[3 * i + 2];
+    if (bwd) {
+        // strand.insert(0, .): backward step k lands at position nb-1-k
+        walk(g, sx, sy, sz, -1.0f, thr, max_steps, [=](int k, float x, float y, float z) {
+            float* p = base + 3 * (nb - 1 - k); p[0] = x; p[1] = y; p[2] = z; });
+    } else {
+        float* p0 = base + 3 * nb; p0[0] = sx; p0[1] = sy; p0[2] = sz;
+        walk(g, sx, sy, sz, 1.0f, thr, max_steps, [=](int k, float x, float y, float z) {
+            float* p = base + 3 * (nb + 1 + k); p[0] = x; p[1] = y; p[2] = z; });
+    }
+}
+
+// HairGrowing.traceFromScalp (HairGrow.py:154-223)
+__global__ void trace_scalp_kernel(Vol g, const float* __restrict__ roots, const float* __restrict__ normals, int64_t n,
+                                   float thr, int max_steps, int max_inner, float* __restrict__ out, int* __restrict__ length) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float px = roots[3 * i], py = roots[3 * i + 1], pz = roots[3 * i + 2];
+    const float n0 = normals[3 * i], n1 = normals[3 * i + 1], n2 = normals[3 * i + 2];
+    // d = (0,1,0); m = min(dot(normal,d)+1, 1); dot = (n0*0 + n1*1) + n2*0 = n1 exactly for finite inputs
+    const float m = fminf(dot3(n0, n1, n2, 0.0f, 1.0f, 0.0f) + 1.0f, 1.0f);
+    float tx = n0 + 0.0f * m, ty = n1 + 1.0f * m, tz = n2 + 0.0f * m;
+    { const float nn = mh_norm3(tx, ty, tz); tx = tx / nn; ty = ty / nn; tz = tz / nn; }
+    float* o = out + (size_t)i * 3 * (max_steps + 1);
+    o[0] = px; o[1] = py; o[2] = pz;
+    int count = 0;
+    bool inner = true;
+    float occ = __ldg(g.v + vox_index(g, px, py, pz)).w;
+    for (;;) {
+        if (occ == 0.0f && !inner) break;
+        const float nx = px + tx, ny = py + ty, nz = pz + tz;
+        const float4 nxt = __ldg(g.v + vox_index(g, nx, ny, nz));
+        float ax = nxt.x, ay = nxt.y, az = nxt.z;
+        if (mh_norm3(ax, ay, az) < 0.1f && inner) {
+            if (dot3(tx, ty, tz, n0, n1, n2) < 0.85f) { ax = tx; ay = ty; az = tz; }
+            else {
+                ax = tx + 0.0f * m; ay = ty + 1.0f * m; az = tz + 0.0f * m;
+                const float nn = mh_norm3(ax, ay, az);
+                ax = ax / nn; ay = ay / nn; az = az / nn;
+            }
+        } else {
+            if (dot3(ax, ay, az, tx, ty, tz) < thr && !inner) {
+                if (dot3(-ax, -ay, -az, tx, ty, tz) < thr) break;
+                ax = -ax; ay = -ay; az = -az;
+            }
+            if (dot3(ax, ay, az, tx, ty, tz) < 0.0f && inner) { ax = -ax; ay = -ay; az = -az; }
+            inner = false;
+        }
+        px = nx; py = ny; pz = nz;
+        tx = ax; ty = ay; tz = az;
+        occ = nxt.w;
+        ++count;
+        o[3 * count] = px; o[3 * count + 1] = py; o[3 * count + 2] = pz;
+        if (count >= max_steps) break;
+        if (count >= max_inner && inner) break;
+    }
+    length[i] = inner ? 0 : count + 1;
+}
+
+// Ordered acceptance: a single warp walks the strands in order (the reference's sequential flag logic).
+// mode 0: gate on flag[seed voxel] >= 3, then flag[voxels] += 1 once per unique voxel (gather-all then scatter-all,
+//         which is what `flag[idx] += 1` does with duplicate indices);  mode 1: no gate, flag[voxels] = 1.
+__global__ void accept_kernel(const float* __restrict__ pts, const int64_t* __restrict__ offsets,
+                              const int* __restrict__ lengths, const float* __restrict__ seeds, int64_t n,
+                              int gx, int gy, int gz, int mode, float* __restrict__ flag, uint8_t* __restrict__ accepted) {
+    const int lane = threadIdx.x;
+    Vol g; g.v = nullptr; g.gx = gx; g.gy = gy; g.gz = gz;
+    for (int64_t i = 0; i < n; ++i) {
+        const int len = lengths[i];
+        bool acc = len > 0;
+        if (acc && mode == 0) {
+            const float f = flag[vox_index(g, seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2])];
+            acc = !(f >= 3.0f);
+        }
+        if (lane == 0) accepted[i] = acc ? 1 : 0;
+        if (!acc) continue;                                     // warp-uniform
+        const float* p = pts + 3 * offsets[i];
+        // len <= 2*256+1 = 513 -> at most 17 rounds of 32
+        float val[17]; int idx[17];
+        int r = 0;
+        for (int k = lane; k < len; k += 32, ++r) {
+            idx[r] = vox_index(g, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+            val[r] = flag[idx[r]];
+        }
+        __syncwarp();
+        r = 0;
+        for (int k = lane; k < len; k += 32, ++r) flag[idx[r]] = (mode == 0) ? val[r] + 1.0f : 1.0f;
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+static int check_vol(const void* volume, int gx, int gy, int gz) {
+    MH_CHECK_ARG(volume && gx > 0 && gy > 0 && gz > 0, "bad volume");
+    return 0;
+}
+
+extern "C" int mh_trace_count(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* seeds,
+                              int64_t n, float thr_dot, int32_t max_steps, int32_t* n_fwd, int32_t* n_bwd) {
+    if (check_vol(volume, gx, gy, gz)) return 1;
+    MH_CHECK_ARG(seeds && n_fwd && n_bwd && max_steps > 0, "bad arguments");
+    if (n == 0) return 0;
+    Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
+    trace_count_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, seeds, n, thr_dot, max_steps, n_fwd, n_bwd);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_trace_write(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* seeds,
+                              int64_t n, float thr_dot, int32_t max_steps, const int32_t* n_fwd, const int32_t* n_bwd,
+                              const int64_t* offsets, int32_t min_len, float* points_out) {
+    if (check_vol(volume, gx, gy, gz)) return 1;
+    MH_CHECK_ARG(seeds && n_fwd && n_bwd && offsets && points_out && max_steps > 0, "bad arguments");
+    if (n == 0) return 0;
+    Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
+    trace_write_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, seeds, n, thr_dot, max_steps, n_fwd, n_bwd, offsets, min_len, points_out);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_trace_from_scalp(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* roots,
+                                   const float* normals, int64_t n, float thr_dot, int32_t max_steps, int32_t max_inner,
+                                   float* points_out, int32_t* length) {
+    if (check_vol(volume, gx, gy, gz)) return 1;
+    MH_CHECK_ARG(roots && normals && points_out && length && max_steps > 0, "bad arguments");
+    if (n == 0) return 0;
+    Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
+    trace_scalp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, roots, normals, n, thr_dot, max_steps, max_inner, points_out, length);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_accept_strands(void* stream, const float* points, const int64_t* offsets, const int32_t* lengths,
+                                 const float* seeds, int64_t n, int32_t gx, int32_t gy, int32_t gz, int32_t mode,
+                                 float* flag, uint8_t* accepted) {
+    MH_CHECK_ARG(points && offsets && lengths && flag && accepted && (mode == 1 || seeds), "null pointer");
+    MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && (mode == 0 || mode == 1), "bad arguments");
+    if (n == 0) return 0;
+    accept_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(points, offsets, lengths, seeds, n, gx, gy, gz, mode, flag, accepted);
+    MH_CHECK_LAUNCH();
+    return 0;
+}

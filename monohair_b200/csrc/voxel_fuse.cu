@@ -1,0 +1,235 @@
+// Multi-view orientation / occupancy fusion into the voxel volume (PMVO.refine, PMVO.py:695-764).
+//
+// The reference builds a Python dict keyed by "x_y_z" and calls compute_points_similarity per voxel.  Here:
+//   1 key      p2v in float64 with round-half-even (PMVO_utils.py:386-404); per-voxel count (atomics)
+//   2 scan     exclusive scan of the dense count volume -> bucket starts
+//   3 fill     point ids into their voxel's bucket
+//   4 fuse     one thread per voxel, x-fastest: empty voxels stream zeros, occupied voxels sort their bucket
+//              back into original point order (first-index tie-break of argmax) and write the medoid.
+// Volume layout: float4 [gz][gy][gx] = {ori.x, -ori.y, -ori.z, occ}: the frame HairGrowing works in
+// (HairGrow.py:45-55), one 16 B fetch per trace step.  Bucket keys use the same z,y,x order so pass 4 reads
+// its 8 B of bucket bounds and writes its 16 B fully coalesced.
+// Bound: HBM streaming.  Algorithmic bytes = n*(12+12) point reads + 4 B/voxel count write+read (x2 for the
+// scan) + 16 B/voxel volume write; 256x256x192: 12.58 M voxels -> 201 MB of volume writes dominate.
+#include "mh_common.cuh"
+
+int mh_exclusive_scan(cudaStream_t st, const int* in, int* out, int64_t n, int* scratch);   // pmvo_refine.cu
+
+namespace {
+
+struct VGrid { double mx, my, mz, vs; int gx, gy, gz; };
+
+// p2v (PMVO_utils.py:386-404): points[:,1:] *= -1 ; round((p - min)/vsize) in float64, half to even; clip.
+__device__ __forceinline__ void p2v(const VGrid& g, float px, float py, float pz, int& x, int& y, int& z) {
+    const double fx = rint(((double)px - g.mx) / g.vs);
+    const double fy = rint((-(double)py - g.my) / g.vs);
+    const double fz = rint((-(double)pz - g.mz) / g.vs);
+    // astype(int32) then clip; values are far inside int32 range for any sane input, clamp in double first
+    x = (int)fmin(fmax(fx, 0.0), (double)(g.gx - 1));
+    y = (int)fmin(fmax(fy, 0.0), (double)(g.gy - 1));
+    z = (int)fmin(fmax(fz, 0.0), (double)(g.gz - 1));
+}
+
+__global__ void key_kernel(VGrid g, const float* __restrict__ pts, int64_t n, int* __restrict__ key,
+                           int* __restrict__ counts, int* __restrict__ vox_index) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x, y, z;
+    p2v(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], x, y, z);
+    const int k = (z * g.gy + y) * g.gx + x;
+    key[i] = k;
+    if (vox_index) vox_index[i] = (x * g.gy + y) * g.gz + z;
+    atomicAdd(counts + k, 1);
+}
+
+__global__ void fill_kernel(const int* __restrict__ key, int64_t n, const int* __restrict__ starts,
+                            int* __restrict__ cursor, int* __restrict__ items) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = key[i];
+    items[starts[k] + atomicAdd(cursor + k, 1)] = (int)i;
+}
+
+// flipped direction of point i (PMVO.py:702-703: ori[ori.y>0] *= -1), normalised like cosine_similarity does
+__device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, float& a, float& b, float& c) {
+    a = dirs[3 * i]; b = dirs[3 * i + 1]; c = dirs[3 * i + 2];
+    if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
+}
+
+__global__ void __launch_bounds__(256)
+fuse_kernel(int64_t nvox, const int* __restrict__ starts, int* __restrict__ items, const float* __restrict__ dirs,
+            float4* __restrict__ volume) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nvox) return;
+    const int s = starts[g], e = starts[g + 1];
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e > s) {
+        const int K = e - s;
+        // restore original point order inside the bucket (atomics filled it in arbitrary order)
+        for (int a = s + 1; a < e; ++a) {
+            const int v = items[a];
+            int b = a - 1;
+            while (b >= s && items[b] > v) { items[b + 1] = items[b]; --b; }
+            items[b + 1] = v;
+        }
+        // medoid under |cos| (compute_points_similarity, PMVO_utils.py:366-382); K == 1 is its own medoid
+        int bk = 0;
+        if (K > 1) {
+            float best = -1e30f;
+            for (int k = 0; k < K; ++k) {
+                float a0, a1, a2;
+                load_dir(dirs, items[s + k], a0, a1, a2);
+                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
+                a0 = a0 / na; a1 = a1 / na; a2 = a2 / na;
+                float sum = 0.0f;
+                for (int j = 0; j < K; ++j) {
+                    float b0, b1, b2;
+                    load_dir(dirs, items[s + j], b0, b1, b2);
+                    const float nb = fmaxf(mh_norm3(b0, b1, b2), 1e-8f);
+                    b0 = b0 / nb; b1 = b1 / nb; b2 = b2 / nb;
+                    sum += fabsf((a0 * b0 + a1 * b1) + a2 * b2);
+                }
+                sum = sum / (float)K;
+                if (sum > best) { best = sum; bk = k; }
+            }
+        }
+        float o0, o1, o2;
+        load_dir(dirs, items[s + bk], o0, o1, o2);
+        out = make_float4(o0, -o1, -o2, 1.0f);
+    }
+    volume[g] = out;
+}
+
+__global__ void overwrite_kernel(VGrid g, const float* __restrict__ pts, const float* __restrict__ dirs, int64_t n,
+                                 int* __restrict__ winner) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x, y, z;
+    p2v(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], x, y, z);
+    atomicMax(winner + (int64_t)(z * g.gy + y) * g.gx + x, (int)i + 1);       // numpy scatter: last writer wins
+}
+__global__ void overwrite_apply_kernel(int64_t nvox, const int* __restrict__ winner, const float* __restrict__ dirs,
+                                       float4* __restrict__ volume) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nvox) return;
+    const int w = winner[g];
+    if (w > 0) {
+        const int i = w - 1;
+        volume[g] = make_float4(dirs[3 * i], -dirs[3 * i + 1], -dirs[3 * i + 2], 1.0f);
+    }
+}
+
+// float4 [gz][gy][gx] -> Occ [gy][gx][gz], Ori [gy][gx][3*gz] float64 (PMVO.py:753-756)
+__global__ void to_mat_kernel(const float4* __restrict__ vol, int gx, int gy, int gz, double* __restrict__ occ,
+                              double* __restrict__ ori) {
+    __shared__ float4 tile[32][33];
+    // transpose (z, x) within a fixed y: read x-fastest, write z-fastest
+    const int y = blockIdx.z;
+    const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+    for (int dz = threadIdx.y; dz < 32; dz += blockDim.y) {
+        const int x = x0 + threadIdx.x, z = z0 + dz;
+        if (x < gx && z < gz) tile[dz][threadIdx.x] = vol[((size_t)z * gy + y) * gx + x];
+    }
+    __syncthreads();
+    for (int dx = threadIdx.y; dx < 32; dx += blockDim.y) {
+        const int x = x0 + dx, z = z0 + threadIdx.x;
+        if (x < gx && z < gz) {
+            const float4 v = tile[threadIdx.x][dx];
+            const size_t o = ((size_t)y * gx + x);
+            occ[o * gz + z] = (double)v.w;
+            ori[o * 3 * gz + z] = (double)v.x;
+            ori[o * 3 * gz + gz + z] = (double)(-v.y);
+            ori[o * 3 * gz + 2 * gz + z] = (double)(-v.z);
+        }
+    }
+}
+__global__ void from_mat_kernel(const double* __restrict__ occ, const double* __restrict__ ori, int gx, int gy, int gz,
+                                float4* __restrict__ vol) {
+    __shared__ float4 tile[32][33];
+    const int y = blockIdx.z;
+    const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+    for (int dx = threadIdx.y; dx < 32; dx += blockDim.y) {
+        const int x = x0 + dx, z = z0 + threadIdx.x;
+        if (x < gx && z < gz) {
+            const size_t o = ((size_t)y * gx + x);
+            // get_ground_truth_3D_ori/occ cast to float32; HairGrowing.__init__ negates channels 1,2
+            const float a = (float)ori[o * 3 * gz + z], b = (float)ori[o * 3 * gz + gz + z], c = (float)ori[o * 3 * gz + 2 * gz + z];
+            tile[threadIdx.x][dx] = make_float4(a, b * -1.0f, c * -1.0f, (float)occ[o * gz + z]);
+        }
+    }
+    __syncthreads();
+    for (int dz = threadIdx.y; dz < 32; dz += blockDim.y) {
+        const int x = x0 + threadIdx.x, z = z0 + dz;
+        if (x < gx && z < gz) vol[((size_t)z * gy + y) * gx + x] = tile[dz][threadIdx.x];
+    }
+}
+
+VGrid make_grid(const double* vmin, double vs, int gx, int gy, int gz) {
+    VGrid g; g.mx = vmin[0]; g.my = vmin[1]; g.mz = vmin[2]; g.vs = vs; g.gx = gx; g.gy = gy; g.gz = gz; return g;
+}
+
+}  // namespace
+
+// workspace: [counts nvox+1][starts nvox+1][cursor nvox][key n][items n][scan scratch]
+extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
+    const int64_t nvox = (int64_t)gx * gy * gz;
+    return 4 * (3 * (nvox + 4) + 2 * n + nvox / 4096 + 64);
+}
+
+extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
+                             const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
+                             void* volume, int32_t* vox_index, void* workspace, int64_t workspace_bytes) {
+    MH_CHECK_ARG(volume && workspace && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
+    MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && voxel_size > 0, "bad grid");
+    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31), "grid or point count too large for int32 keys");
+    MH_CHECK_ARG(workspace_bytes >= mh_voxel_fuse_workspace_bytes(n, gx, gy, gz), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nvox = (int64_t)gx * gy * gz;
+    const VGrid g = make_grid(voxel_min_host, voxel_size, gx, gy, gz);
+    int* counts = reinterpret_cast<int*>(workspace);
+    int* starts = counts + (nvox + 4);
+    int* cursor = starts + (nvox + 4);
+    int* key = cursor + (nvox + 4);
+    int* items = key + n;
+    int* scratch = items + n;
+    cudaMemsetAsync(counts, 0, sizeof(int) * (nvox + 1), st);
+    cudaMemsetAsync(cursor, 0, sizeof(int) * nvox, st);
+    if (n > 0) key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, n, key, counts, vox_index);
+    mh_exclusive_scan(st, counts, starts, nvox, scratch);
+    if (n > 0) fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, starts, cursor, items);
+    fuse_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, st>>>(nvox, starts, items, dirs, reinterpret_cast<float4*>(volume));
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_voxel_overwrite(void* stream, const float* points, const float* dirs, int64_t n,
+                                     const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy,
+                                     int32_t gz, void* volume, void* winner_ws /* int32 [gz*gy*gx] */) {
+    MH_CHECK_ARG(volume && winner_ws && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nvox = (int64_t)gx * gy * gz;
+    const VGrid g = make_grid(voxel_min_host, voxel_size, gx, gy, gz);
+    cudaMemsetAsync(winner_ws, 0, sizeof(int) * nvox, st);
+    overwrite_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, dirs, n, reinterpret_cast<int*>(winner_ws));
+    overwrite_apply_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, st>>>(nvox, reinterpret_cast<int*>(winner_ws), dirs,
+                                                                          reinterpret_cast<float4*>(volume));
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_volume_to_mat(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, double* occ, double* ori) {
+    MH_CHECK_ARG(volume && occ && ori && gx > 0 && gy > 0 && gz > 0, "bad arguments");
+    dim3 grid((gx + 31) / 32, (gz + 31) / 32, gy), block(32, 8);
+    to_mat_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(volume), gx, gy, gz, occ, ori);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_volume_from_mat(void* stream, const double* occ, const double* ori, int32_t gx, int32_t gy, int32_t gz, void* volume) {
+    MH_CHECK_ARG(volume && occ && ori && gx > 0 && gy > 0 && gz > 0, "bad arguments");
+    dim3 grid((gx + 31) / 32, (gz + 31) / 32, gy), block(32, 8);
+    from_mat_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(occ, ori, gx, gy, gz, reinterpret_cast<float4*>(volume));
+    MH_CHECK_LAUNCH();
+    return 0;
+}

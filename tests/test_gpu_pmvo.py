@@ -1,0 +1,208 @@
+"""GPU parity tests of the PMVO path: CUDA kernels (through the C ABI) against
+  (a) golden vectors produced by the unmodified reference (tests/golden/*.npz) and
+  (b) the CPU oracle (oracle/pmvo_oracle.py) on the same seeded inputs.
+
+Bars: pixel / voxel indices, visibility values, surface / filter masks, base-view selection: bit-exact.
+Floats: min_loss <= 1e-5 abs, direction <= 1e-4 L-inf -- the kernels follow the reference's fp32
+operation order, so in practice they are bit-identical for almost every point; the exact-match rate is printed.
+"""
+import numpy as np
+import pytest
+import torch
+from scipy.spatial import KDTree
+
+from golden_util import load, scene_of
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["pmvo_p7", "pmvo_p5_ties"]
+LOSS_ATOL = 1e-5
+ORI_LINF = 1e-4
+
+
+def build(g, sc):
+    from monohair_b200.camera import cameras_from_scene
+    from monohair_b200.pmvo import PMVO
+    Ori, Conf = sc.ref_ori_conf()
+    return PMVO(cameras_from_scene(sc), sc.ref_depths(), Ori, Conf, sc.ref_masks(), device="cuda:0",
+                image_size=[sc.H, sc.W], patch_size=int(g["patch"]), visible_threshold=1,
+                conf_threshold=float(g["conf_thr"]))
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    g = load(request.param)
+    sc = scene_of(g)
+    return g, sc, build(g, sc)
+
+
+def test_filter_points_vs_reference_golden(case):
+    g, sc, pmvo = case
+    pts = torch.from_numpy(g["points"][: int(g["n_covered"])]).float()
+    s, sp, f = pmvo.filter_points(pts)
+    assert np.array_equal(s.cpu().numpy(), g["surface_index"])
+    assert np.array_equal(f.cpu().numpy(), g["filter_index"])
+    assert np.array_equal(sp.cpu().numpy(), pts.numpy()[g["surface_index"]])
+
+
+def test_filter_counters_and_centre_values_bit_exact_vs_oracle(case):
+    from oracle import pmvo_oracle as O
+    g, sc, pmvo = case
+    vm = O.ViewMaps.from_scene(sc)
+    pts = torch.from_numpy(g["points"][:3000]).float()
+    _, _, cnt_o = O.filter_points(vm, pts, int(g["patch"]), 1, float(g["conf_thr"]))
+    _, cnt = pmvo.filter_counters(pts)
+    assert torch.equal(cnt.cpu(), cnt_o)
+    st = O.compute_visible_and_ori(vm, pts[:500], int(g["patch"]))
+    pmvo.Compute_Visible_and_Ori(pts[:500])
+    assert torch.equal(pmvo.visible.cpu(), st["visible"])
+    assert torch.equal(pmvo.Conf.cpu(), st["Conf"])
+    assert torch.equal(pmvo.Ori.cpu(), st["Ori"])
+    unv = pmvo.compute_unvisible_points(pts)
+    assert torch.equal(unv.cpu(), O.compute_unvisible_points(vm, pts))
+
+
+def test_packed_via_u8_path_identical(case):
+    from monohair_b200.camera import cameras_from_scene
+    from monohair_b200.pmvo import PMVO
+    g, sc, pmvo = case
+    p2 = PMVO.from_u8(cameras_from_scene(sc), sc.depth, sc.ori_gray, sc.conf_u8, sc.mask_u8, device="cuda:0",
+                      image_size=[sc.H, sc.W], patch_size=int(g["patch"]), visible_threshold=1,
+                      conf_threshold=float(g["conf_thr"]))
+    assert torch.equal(p2.mapC, pmvo.mapC)
+    assert torch.equal(p2.mapP, pmvo.mapP)
+
+
+def test_forward_vs_reference_golden(case):
+    g, sc, pmvo = case
+    _, ori, loss, hc, dbg = pmvo.forward(g["fwd_points"], debug=True)
+    ori, loss, hc = ori.cpu().numpy(), loss.cpu().numpy(), hc.cpu().numpy()
+    # base views: same order as torch.topk on CPU (ties included)
+    assert np.array_equal(dbg["base_val"].cpu().numpy(), g["fwd_base_val"])
+    assert np.array_equal(dbg["base_idx"].cpu().numpy().astype(np.int64), g["fwd_base_idx"])
+    exact = (loss == g["fwd_loss"]) & np.all(ori == g["fwd_ori"], axis=1)
+    print(f"\nforward: {exact.mean() * 100:.2f}% of {len(loss)} points bit-identical to the reference; "
+          f"max |dloss|={np.abs(loss - g['fwd_loss']).max():.3g} "
+          f"max |dori|={np.abs(ori - g['fwd_ori']).max():.3g}")
+    assert np.abs(loss - g["fwd_loss"]).max() <= LOSS_ATOL
+    assert np.array_equal(hc, g["fwd_hc"])
+    d = np.abs(ori - g["fwd_ori"]).max(axis=1)
+    bad = d > ORI_LINF
+    # a different (equally good within fp noise) depth sample may be picked when two samples' losses tie to ~1e-7
+    assert bad.mean() <= 0.01, f"{bad.sum()} of {len(bad)} directions differ by more than {ORI_LINF}"
+    assert exact.mean() >= 0.95
+
+
+def test_forward_per_base_losses_vs_oracle(case):
+    from oracle import pmvo_oracle as O
+    g, sc, pmvo = case
+    vm = O.ViewMaps.from_scene(sc)
+    n = 64
+    _, o_o, l_o, hc_o, dbg_o = O.forward(vm, g["fwd_points"][:n], int(g["patch"]), float(g["conf_thr"]), debug=True)
+    _, ori, loss, hc, dbg = pmvo.forward(g["fwd_points"][:n], debug=True)
+    lb = dbg["loss_b"].cpu().numpy()
+    ab = dbg["arg_b"].cpu().numpy()
+    valid = ab >= 0
+    lo = torch.stack(dbg_o["loss_b"]).numpy()
+    ao = torch.stack(dbg_o["arg"]).numpy()
+    assert np.abs(lb[valid] - lo[valid]).max() <= LOSS_ATOL
+    print(f"\nper-base: losses bit-identical {np.mean(lb[valid] == lo[valid]) * 100:.2f}%, argmin identical "
+          f"{np.mean(ab[valid] == ao[valid]) * 100:.2f}%")
+    assert np.mean(ab[valid] == ao[valid]) >= 0.97
+    # bases the reference ignores (base conf <= 0, b > 0) are skipped by the kernel
+    bc = dbg_o["base_conf"].numpy()
+    assert np.array_equal(valid[1:], bc[1:] > 0)
+
+
+def test_refine_voxelise_vs_reference_golden(case, tmp_path):
+    import types
+    import scipy.io
+    from monohair_b200 import pmvo as P
+    g, sc, pmvo = case
+    scalp = g["scalp"]
+    P.scalp_tree = KDTree(data=scalp)
+    P.scalp_max = scalp.max(0)
+    td = str(tmp_path)
+    a = types.SimpleNamespace(output_path=td, save_path=td + "/refine", device="cuda:0",
+                              PMVO=types.SimpleNamespace(visible_threshold=1), data=types.SimpleNamespace(root=td))
+    import os
+    os.makedirs(a.save_path, exist_ok=True)
+    P.refine(g["fwd_points"].astype(np.float32), g["fwd_ori"].copy(), g["fwd_loss"].copy(), pmvo,
+             g["filter_unvisible_in"].copy(), a, infer_inner=False, threshold=float(g["thr"]), genrate_ori_only=False)
+    so = np.load(td + "/refine/select_o.npy")
+    ml = np.load(td + "/refine/min_loss.npy")
+    print(f"\nrefine: select_o identical rows {np.mean(np.all(so == g['ref_select_o'], 1)) * 100:.2f}%, "
+          f"loss max diff {np.abs(ml - g['ref_min_loss']).max():.3g}")
+    assert np.abs(ml - g["ref_min_loss"]).max() <= LOSS_ATOL
+    assert np.mean(np.all(so == g["ref_select_o"], 1)) >= 0.98
+    fu_p = np.load(td + "/refine/filter_unvisible.npy")
+    fu_o = np.load(td + "/refine/filter_unvisible_ori.npy")
+    assert np.array_equal(fu_p, g["ref_fu_points"])                    # head filter decisions: exact
+    assert np.mean(np.all(fu_o == g["ref_fu_ori"], 1)) >= 0.98
+    Occ = scipy.io.loadmat(td + "/refine/Occ3D.mat")["Occ"]
+    Ori = scipy.io.loadmat(td + "/refine/Ori3D.mat")["Ori"]
+    assert Occ.dtype == np.float64 and Ori.dtype == np.float64
+    assert tuple(Ori.shape) == tuple(g["mat_ori_shape"])
+    nz = np.argwhere(Occ > 0)
+    assert np.array_equal(nz, g["mat_occ_nz"])                         # occupancy: bit-exact
+    Z = Occ.shape[2]
+    vals = np.stack([Ori[i, j, [k, k + Z, k + 2 * Z]] for i, j, k in nz])
+    same = np.all(vals == g["mat_ori_nz"], axis=1)
+    print(f"orientation volume: {same.mean() * 100:.2f}% of {len(nz)} occupied voxels bit-identical; "
+          f"L-inf over the rest {np.abs(vals - g['mat_ori_nz'])[~same].max() if (~same).any() else 0:.3g}")
+    assert same.mean() >= 0.97
+    assert np.all(Ori.reshape(Occ.shape[0], Occ.shape[1], 3, Z).transpose(0, 1, 3, 2)[Occ == 0] == 0)
+
+
+def test_voxel_fuse_vs_oracle_exact(case):
+    from oracle import pmvo_oracle as O
+    from monohair_b200 import pmvo as P
+    g, sc, pmvo = case
+    rng = np.random.default_rng(5)
+    n = 6000
+    pts = (g["fwd_points"][rng.integers(0, len(g["fwd_points"]), n)] + rng.normal(0, 2e-3, (n, 3))).astype(np.float32)
+    dirs = rng.normal(size=(n, 3)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    # exact .5 boundaries of the float64 index math (np.round half-even)
+    pts[:50, 0] = (-0.32 + (np.arange(50) + 100.5) * 0.0025).astype(np.float32)
+    occ_o, ori_o = O.voxel_fuse(pts.copy(), dirs.copy())
+    vol, vidx = P.voxel_fuse(pts, dirs, "cuda:0", return_index=True)
+    x, y, z = O.p2v(pts.astype(np.float64).copy() * 1.0, np.array([-0.32, -0.32, -0.24]), 0.005 / 2, np.array([256, 256, 192]))
+    assert np.array_equal(vidx.cpu().numpy(), (x.astype(np.int64) * 256 + y) * 192 + z)
+    v = vol.cpu().numpy()                                              # [gz,gy,gx,4]
+    occ = v[..., 3].transpose(2, 1, 0)
+    assert np.array_equal(occ, occ_o.astype(np.float32))
+    ori = np.stack([v[..., 0], -v[..., 1], -v[..., 2]], -1).transpose(2, 1, 0, 3)
+    same = np.all(ori == ori_o.astype(np.float32), axis=-1)
+    assert same[occ_o > 0].mean() >= 0.995
+    assert same[occ_o == 0].all()
+    om, orim = P.volume_to_mat(vol)
+    mo, mori = O.mat_layout(occ.astype(np.float64), ori.astype(np.float64))
+    assert np.array_equal(om.cpu().numpy(), mo) and np.array_equal(orim.cpu().numpy(), mori)
+
+
+def test_knn_exact_vs_kdtree():
+    from monohair_b200 import pmvo as P
+    rng = np.random.default_rng(0)
+    ref = (rng.normal(size=(20000, 3)) * np.array([0.1, 0.13, 0.11])).astype(np.float32)
+    ref /= np.maximum(np.linalg.norm(ref / np.array([0.1, 0.13, 0.11], np.float32), axis=1, keepdims=True), 1e-6)
+    ref += rng.normal(0, 2e-3, ref.shape).astype(np.float32)
+    q = np.concatenate([ref[:3000], (ref[:500] + 0.01).astype(np.float32), np.array([[1, 1, 1], [-1, 0, 0]], np.float32)])
+    d_ref, i_ref = KDTree(data=ref).query(q, 100)
+    idx = P.knn(torch.from_numpy(ref).cuda(), torch.from_numpy(q).cuda(), 100, torch.device("cuda:0")).cpu().numpy()
+    dd = np.linalg.norm(ref[idx].astype(np.float64) - q[:, None, :].astype(np.float64), axis=-1)
+    assert np.allclose(dd, d_ref, rtol=0, atol=1e-12)
+    assert np.mean(idx == i_ref) > 0.9999
+
+
+def test_empty_and_single_inputs(case):
+    g, sc, pmvo = case
+    s, sp, f = pmvo.filter_points(torch.zeros((0, 3)))
+    assert s.numel() == 0 and sp.shape == (0, 3) and f.numel() == 0
+    p, o, l, hc = pmvo.forward(np.zeros((0, 3)))
+    assert o.shape == (0, 3) and l.numel() == 0
+    p, o, l, hc = pmvo.forward(g["fwd_points"][:1])
+    assert np.abs(l.cpu().numpy() - g["fwd_loss"][:1]).max() <= LOSS_ATOL
+    far = np.array([[5.0, 5.0, 5.0]])                                   # out of every image: invisible everywhere
+    s, sp, f = pmvo.filter_points(torch.from_numpy(far).float())
+    assert not bool(s[0]) and not bool(f[0])
