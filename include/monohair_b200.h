@@ -36,6 +36,8 @@ typedef struct mh_views {
 
 const char* mh_last_error(void);
 int mh_version(void);
+/* number of CUDA kernels this library has launched so far in the process (bench.py: gpu_launches) */
+int64_t mh_launch_count(void);
 
 /* ---- views ------------------------------------------------------------------------------------------- */
 /* Fill cam[v] from host data: pose = world->camera 4x4 row-major (Camera.pose), ndc_prj = {fx,fy,cx,cy}

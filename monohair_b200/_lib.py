@@ -33,6 +33,7 @@ VP = C.POINTER(MhViews)
 _SIGS = {
     "mh_last_error": (C.c_char_p, []),
     "mh_version": (C.c_int, []),
+    "mh_launch_count": (i64, []),
     "mh_views_pack_camera_host": (C.c_int, [p, p, p, p]),
     "mh_views_pack": (C.c_int, [p, i32, i32, i32, i32, p, i32, p, p, p, i32, p, p]),
     "mh_views_pack_u8": (C.c_int, [p, i32, i32, i32, i32, p, i32, p, p, p, p, p, p, p, p]),

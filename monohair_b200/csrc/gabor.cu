@@ -214,8 +214,11 @@ extern "C" int mh_gabor_orientation(void* stream, const float* image, int32_t H,
     cudaMemsetAsync(gmax, 0, 4, st);
     dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H), block(TX, TY);
     gabor_resp_kernel<<<grid, block, 0, st>>>(image, H, W, bank, nf, resp);
+    MH_COUNT_LAUNCH();
     gabor_epilogue_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, st>>>(resp, HW, nf, orient, var, gmax);
+    MH_COUNT_LAUNCH();
     gabor_finish_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, st>>>(HW, orient, var, gmax, clamp_low, clamp_high, conf, two_channel);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -227,6 +230,7 @@ extern "C" int mh_filterbank_wrap_f64(void* stream, const double* image, int32_t
     const int tw = 16 + ksize - 1;
     dim3 grid((W + 15) / 16, (H + 15) / 16), block(16, 16);
     wrap_bank_kernel<<<grid, block, sizeof(double) * tw * tw, (cudaStream_t)stream>>>(image, H, W, bank, nf, ksize, out_abs);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -241,10 +245,13 @@ extern "C" int mh_dog_f64(void* stream, const double* image, int32_t H, int32_t 
     dim3 grid((W + 127) / 128, H), block(128);
     // gaussian_filter filters axis 0 first, then axis 1
     gauss1d_kernel<<<grid, block, 0, st>>>(image, H, W, k_lo, r_lo, 0, t0);
+    MH_COUNT_LAUNCH();
     gauss1d_kernel<<<grid, block, 0, st>>>(t0, H, W, k_lo, r_lo, 1, out);          // out = low
     gauss1d_kernel<<<grid, block, 0, st>>>(image, H, W, k_hi, r_hi, 0, t0);
+    MH_COUNT_LAUNCH();
     gauss1d_kernel<<<grid, block, 0, st>>>(t0, H, W, k_hi, r_hi, 1, t1);           // t1 = high
     sub_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, st>>>(out, t1, HW, out);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }

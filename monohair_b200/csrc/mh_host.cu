@@ -15,6 +15,8 @@ void mh_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+long long g_mh_launches = 0;
+extern "C" int64_t mh_launch_count(void) { return (int64_t)g_mh_launches; }
 extern "C" const char* mh_last_error(void) { return g_err; }
 extern "C" int mh_version(void) { return 100; }
 

@@ -101,18 +101,20 @@ int check_views(const mh_views* vw) {
 extern "C" int mh_filter_count(void* stream, const mh_views* views, const float* points, int64_t N,
                                float visible_threshold, float conf_threshold, float* counters) {
     if (check_views(views)) return 1;
-    MH_CHECK_ARG(points && counters && N >= 0, "bad arguments");
     if (N == 0) return 0;
+    MH_CHECK_ARG(points && counters && N > 0, "bad arguments");
     count_kernel<FILTER><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         *views, points, N, visible_threshold, conf_threshold, counters);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int mh_filter_decide(void* stream, const float* counters, int64_t N, uint8_t* surface, uint8_t* filter) {
-    MH_CHECK_ARG(counters && surface && filter && N >= 0, "bad arguments");
     if (N == 0) return 0;
+    MH_CHECK_ARG(counters && surface && filter && N > 0, "bad arguments");
     decide_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counters, N, surface, filter);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -120,10 +122,11 @@ extern "C" int mh_filter_decide(void* stream, const float* counters, int64_t N, 
 extern "C" int mh_visible_count(void* stream, const mh_views* views, const float* points, int64_t N,
                                 float dz_threshold, float* count) {
     if (check_views(views)) return 1;
-    MH_CHECK_ARG(points && count && N >= 0, "bad arguments");
     if (N == 0) return 0;
+    MH_CHECK_ARG(points && count && N > 0, "bad arguments");
     count_kernel<VISCOUNT><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         *views, points, N, dz_threshold, 0.0f, count);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -131,10 +134,11 @@ extern "C" int mh_visible_count(void* stream, const mh_views* views, const float
 extern "C" int mh_head_count(void* stream, const mh_views* views, const float* points, int64_t N,
                              float visible_threshold, float* counters) {
     if (check_views(views)) return 1;
-    MH_CHECK_ARG(points && counters && N >= 0, "bad arguments");
     if (N == 0) return 0;
+    MH_CHECK_ARG(points && counters && N > 0, "bad arguments");
     count_kernel<HEAD><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         *views, points, N, visible_threshold, 0.0f, counters);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -180,10 +184,11 @@ __global__ void head_decide_kernel(const float* __restrict__ c, const double* __
 extern "C" int mh_centre_gather(void* stream, const mh_views* views, const float* points, int64_t N, float* visible,
                                 float* ori, float* conf, float* mask, int32_t* rowcol) {
     if (check_views(views)) return 1;
-    MH_CHECK_ARG(points && visible && ori && conf && N >= 0, "bad arguments");
     if (N == 0) return 0;
+    MH_CHECK_ARG(points && visible && ori && conf && N > 0, "bad arguments");
     dim3 grid((unsigned)((N + 255) / 256), views->V);
     centre_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*views, points, N, visible, ori, conf, mask, rowcol);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -194,6 +199,7 @@ extern "C" int mh_head_decide(void* stream, const float* counters, const double*
     if (N == 0) return 0;
     head_decide_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counters, scalp_dist, points, N,
                                                                                    dist_threshold, z_threshold, filter);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }

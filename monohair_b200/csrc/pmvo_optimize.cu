@@ -325,7 +325,8 @@ extern "C" int mh_pmvo_optimize(void* stream, const mh_views* vw, const float* p
                                 int32_t* dbg_base_idx, float* dbg_base_val, float* dbg_best_sample,
                                 float* dbg_loss_b, int32_t* dbg_arg_b, void* workspace, int64_t workspace_bytes) {
     MH_CHECK_ARG(vw && vw->mapC && vw->mapP && vw->cam, "null views");
-    MH_CHECK_ARG(points && offsets && ori && loss && high_conf && workspace, "null pointer");
+    if (N == 0) return 0;
+    MH_CHECK_ARG(points && offsets && ori && loss && high_conf && workspace && N > 0, "null pointer");
     MH_CHECK_ARG(workspace_bytes >= 256, "workspace too small");
     MH_CHECK_ARG(vw->V >= MH_TOPK, "PMVO.forward needs at least 20 views (torch.topk(...,20), PMVO.py:341)");
     MH_CHECK_ARG(S >= 1 && S <= 32 * MAX_ROUNDS, "num_sample must be in [1,128]");
@@ -353,6 +354,7 @@ extern "C" int mh_pmvo_optimize(void* stream, const mh_views* vw, const float* p
     optimize_kernel<<<(unsigned)grid, OPT_THREADS, smem, (cudaStream_t)stream>>>(
         *vw, points, N, offsets, S, conf_threshold, ori, loss, high_conf, dbg_base_idx, dbg_base_val,
         dbg_best_sample, dbg_loss_b, dbg_arg_b, reinterpret_cast<unsigned long long*>(workspace));
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }

@@ -178,8 +178,11 @@ int mh_exclusive_scan(cudaStream_t st, const int* in, int* out, int64_t n, int* 
     const int64_t per = (int64_t)SCAN_BLOCK * SCAN_ITEMS;
     const int nb = (int)((n + per - 1) / per);
     scan_local_kernel<<<nb, SCAN_BLOCK, 0, st>>>(in, out, n, scratch);
+    MH_COUNT_LAUNCH();
     scan_sums_kernel<<<1, SCAN_BLOCK, 0, st>>>(scratch, nb, out + n);
+    MH_COUNT_LAUNCH();
     scan_add_kernel<<<nb, SCAN_BLOCK, 0, st>>>(out, n, scratch);
+    MH_COUNT_LAUNCH();
     return 0;
 }
 
@@ -360,8 +363,8 @@ medoid_gather_kernel(const float* __restrict__ ori, const int* __restrict__ nbr,
 extern "C" int mh_pmvo_refine_loss(void* stream, const mh_views* vw, const float* points, const float* dir,
                                    int64_t N, float conf_threshold, float* loss) {
     MH_CHECK_ARG(vw && vw->mapC && vw->mapP && vw->cam, "null views");
-    MH_CHECK_ARG(points && dir && loss && N >= 0, "bad arguments");
     if (N == 0) return 0;
+    MH_CHECK_ARG(points && dir && loss && N > 0, "bad arguments");
     const size_t smem = sizeof(MhCam) * vw->V + sizeof(float) * 2 * vw->V * RL_WARPS;
     MH_CHECK_ARG(smem <= 200 * 1024, "too many views");
     cudaFuncSetAttribute(refine_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -369,6 +372,7 @@ extern "C" int mh_pmvo_refine_loss(void* stream, const mh_views* vw, const float
     const int64_t cap = (int64_t)mh_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     refine_loss_kernel<<<(unsigned)blocks, RL_WARPS * 32, smem, (cudaStream_t)stream>>>(*vw, points, dir, N, conf_threshold, loss);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -410,12 +414,15 @@ extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float
     cudaMemsetAsync(counts, 0, sizeof(int) * (ncell + 1), st);
     cudaMemsetAsync(cursor, 0, sizeof(int) * ncell, st);
     knn_count_kernel<<<(unsigned)((n_ref + 255) / 256), 256, 0, st>>>(g, ref, n_ref, counts, cell_of_pt);
+    MH_COUNT_LAUNCH();
     mh_exclusive_scan(st, counts, starts, ncell, scratch);
     knn_fill_kernel<<<(unsigned)((n_ref + 255) / 256), 256, 0, st>>>(cell_of_pt, n_ref, starts, cursor, items);
+    MH_COUNT_LAUNCH();
     int64_t blocks = (n_query + KNN_WARPS - 1) / KNN_WARPS;
     const int64_t cap = (int64_t)mh_sm_count() * 32;
     if (blocks > cap) blocks = cap;
     knn_query_kernel<<<(unsigned)blocks, KNN_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -424,6 +431,7 @@ extern "C" int mh_nn_dist(void* stream, const double* ref, int64_t n_ref, const 
     MH_CHECK_ARG(ref && query && dist && n_ref >= 1, "bad arguments");
     if (n_query == 0) return 0;
     nn_dist_kernel<<<(unsigned)((n_query + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ref, n_ref, query, n_query, dist);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -437,6 +445,7 @@ extern "C" int mh_medoid_gather(void* stream, const float* ori, const int32_t* n
     const int64_t cap = (int64_t)mh_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     medoid_gather_kernel<<<(unsigned)blocks, MED_WARPS * 32, smem, (cudaStream_t)stream>>>(ori, nbr, n, K, out, out_k);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -464,6 +473,7 @@ extern "C" int mh_refine_update(void* stream, const float* center, const float* 
     MH_CHECK_ARG(center && upd_loss && head_filter && ori && loss && n >= 0, "bad arguments");
     if (n == 0) return 0;
     refine_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(center, upd_loss, head_filter, n, ori, loss);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }

@@ -59,6 +59,7 @@ extern "C" int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int3
         mapP[i] = make_float4(o.x, o.y, __ldg(conf + i), cmax);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -84,6 +85,7 @@ extern "C" int mh_views_pack_u8(void* stream, int32_t v, int32_t H, int32_t W, i
         mapP[i] = make_float4(__ldg(ori_lut + 2 * g), __ldg(ori_lut + 2 * g + 1), __ldg(conf_lut + __ldg(conf_u8 + i)), cmax);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }

@@ -170,6 +170,7 @@ extern "C" int mh_trace_count(void* stream, const void* volume, int32_t gx, int3
     if (n == 0) return 0;
     Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
     trace_count_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, seeds, n, thr_dot, max_steps, n_fwd, n_bwd);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -182,6 +183,7 @@ extern "C" int mh_trace_write(void* stream, const void* volume, int32_t gx, int3
     if (n == 0) return 0;
     Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
     trace_write_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, seeds, n, thr_dot, max_steps, n_fwd, n_bwd, offsets, min_len, points_out);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -194,6 +196,7 @@ extern "C" int mh_trace_from_scalp(void* stream, const void* volume, int32_t gx,
     if (n == 0) return 0;
     Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
     trace_scalp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, roots, normals, n, thr_dot, max_steps, max_inner, points_out, length);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -205,6 +208,7 @@ extern "C" int mh_accept_strands(void* stream, const float* points, const int64_
     MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && (mode == 0 || mode == 1), "bad arguments");
     if (n == 0) return 0;
     accept_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(points, offsets, lengths, seeds, n, gx, gy, gz, mode, flag, accepted);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }

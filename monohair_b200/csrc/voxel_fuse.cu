@@ -194,10 +194,11 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
     int* scratch = items + n;
     cudaMemsetAsync(counts, 0, sizeof(int) * (nvox + 1), st);
     cudaMemsetAsync(cursor, 0, sizeof(int) * nvox, st);
-    if (n > 0) key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, n, key, counts, vox_index);
+    if (n > 0) { key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, n, key, counts, vox_index); MH_COUNT_LAUNCH(); }
     mh_exclusive_scan(st, counts, starts, nvox, scratch);
-    if (n > 0) fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, starts, cursor, items);
+    if (n > 0) { fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, starts, cursor, items); MH_COUNT_LAUNCH(); }
     fuse_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, st>>>(nvox, starts, items, dirs, reinterpret_cast<float4*>(volume));
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -212,8 +213,10 @@ extern "C" int mh_voxel_overwrite(void* stream, const float* points, const float
     const VGrid g = make_grid(voxel_min_host, voxel_size, gx, gy, gz);
     cudaMemsetAsync(winner_ws, 0, sizeof(int) * nvox, st);
     overwrite_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, dirs, n, reinterpret_cast<int*>(winner_ws));
+    MH_COUNT_LAUNCH();
     overwrite_apply_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, st>>>(nvox, reinterpret_cast<int*>(winner_ws), dirs,
                                                                           reinterpret_cast<float4*>(volume));
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -222,6 +225,7 @@ extern "C" int mh_volume_to_mat(void* stream, const void* volume, int32_t gx, in
     MH_CHECK_ARG(volume && occ && ori && gx > 0 && gy > 0 && gz > 0, "bad arguments");
     dim3 grid((gx + 31) / 32, (gz + 31) / 32, gy), block(32, 8);
     to_mat_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(volume), gx, gy, gz, occ, ori);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -230,6 +234,7 @@ extern "C" int mh_volume_from_mat(void* stream, const double* occ, const double*
     MH_CHECK_ARG(volume && occ && ori && gx > 0 && gy > 0 && gz > 0, "bad arguments");
     dim3 grid((gx + 31) / 32, (gz + 31) / 32, gy), block(32, 8);
     from_mat_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(occ, ori, gx, gy, gz, reinterpret_cast<float4*>(volume));
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }

@@ -1,0 +1,182 @@
+"""In-memory PMVO job: what PMVO.py's __main__ does between "maps loaded" and "Ori3D.mat / Occ3D.mat written"
+(PMVO.py:847-872), without the intermediate .npy round trips.  The CLI entry point (PMVO.py at the repo root)
+wraps this and writes the reference's files; bench.py times it.
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL): every rank holds all views; the candidate points are
+sharded by index for filter_points / forward (no data-path collective, results all-gathered), the kNN of the
+refine stage is sharded by query, and the voxel fusion is sharded by voxel slab with ONE all-reduce(SUM) of the
+fused volume (disjoint support, so the sum is exact) -- SURVEY.md §8e.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import pmvo as P
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def _shard(n, rank, world):
+    """contiguous shard [a,b) of n items for `rank`."""
+    per = (n + world - 1) // world
+    a = min(rank * per, n)
+    return a, min(a + per, n)
+
+
+def _all_gather_rows(t, n_total, world, dist):
+    """all_gather of equally-padded row shards -> first n_total rows."""
+    per = (n_total + world - 1) // world
+    pad = per - t.size(0)
+    if pad > 0:
+        t = torch.cat([t, t.new_zeros((pad,) + tuple(t.shape[1:]))], 0)
+    out = t.new_empty((world * per,) + tuple(t.shape[1:]))
+    dist.all_gather_into_tensor(out, t.contiguous())
+    return out[:n_total]
+
+
+def filter_stage(pm, cand, n_cov=None):
+    """filter_negative_points on device.  cand float32 [N,3] device tensor -> (surface mask, filter mask) over
+    the covered prefix (reference chunk arithmetic, §9-R5)."""
+    dist = _dist()
+    N = cand.size(0)
+    if n_cov is None:
+        step = 30 if N % 30 == 0 else 31
+        n_cov = min(step * (N // 30), N)
+    cand = cand[:n_cov]
+    if dist is None:
+        _, cnt = pm.filter_counters(cand)
+    else:
+        r, w = dist.get_rank(), dist.get_world_size()
+        a, b = _shard(n_cov, r, w)
+        _, cnt_local = pm.filter_counters(cand[a:b])
+        cnt = _all_gather_rows(cnt_local.t().contiguous(), n_cov, w, dist).t().contiguous()
+    return pm.filter_decide(cnt)
+
+
+def forward_stage(pm, pts):
+    dist = _dist()
+    if dist is None:
+        _, ori, loss, hc = pm.forward(pts)
+        return ori, loss, hc
+    r, w = dist.get_rank(), dist.get_world_size()
+    n = pts.size(0)
+    a, b = _shard(n, r, w)
+    _, ori, loss, hc = pm.forward(pts[a:b])
+    packed = torch.cat([ori, loss[:, None], hc[:, None].float()], 1)
+    packed = _all_gather_rows(packed, n, w, dist)
+    return packed[:, :3].contiguous(), packed[:, 3].contiguous(), packed[:, 4] > 0.5
+
+
+def knn_stage(ref, query, k, dev):
+    dist = _dist()
+    if dist is None:
+        return P.knn(ref, query, k, dev)
+    r, w = dist.get_rank(), dist.get_world_size()
+    n = query.size(0)
+    a, b = _shard(n, r, w)
+    idx = P.knn(ref, query[a:b].contiguous(), k, dev) if b > a else torch.empty((0, k), dtype=torch.int32, device=dev)
+    return _all_gather_rows(idx, n, w, dist)
+
+
+def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
+    """PMVO.refine step (i): sharded kNN, then the chunk-sequential medoid / re-score / update (replicated: it is
+    Gauss-Seidel across chunks, §9-R7, and tiny next to forward)."""
+    dev = pm.device
+    n = pts.size(0)
+    o, l = ori.clone(), loss.clone()
+    if n == 0:
+        return o, l
+    nbr = knn_stage(pts, pts, k, dev)
+    with torch.cuda.device(dev):
+        st = stream_ptr(dev)
+        for i in range(n // sub_num + 1):
+            a, b = i * sub_num, min((i + 1) * sub_num, n)
+            if b <= a:
+                continue
+            center = P.medoid_gather(o, nbr[a:b], dev)
+            upd = pm.refine_loss_raw(pts[a:b], center)
+            filt = pm.filter_head_points(pts[a:b], pm.visible_threshold)
+            check(lib().mh_refine_update(st, ptr(center), ptr(upd), ptr(filt.to(torch.uint8)), b - a, ptr(o[a:b]), ptr(l[a:b])),
+                  "mh_refine_update")
+    return o, l
+
+
+def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE):
+    """Voxel fusion; with several ranks each fuses the points whose voxel z-slab it owns into a zeroed volume and
+    the volumes are summed with one all-reduce over NVLink."""
+    dev = pm.device
+    dist = _dist()
+    if dist is None:
+        return P.voxel_fuse(pts, dirs, dev, grid, voxel_min, voxel_size)
+    r, w = dist.get_rank(), dist.get_world_size()
+    gz = int(grid[2])
+    # owner by z slab of the voxel index; float64 index math identical to p2v (points[:,2] flipped)
+    z = torch.round((-(pts[:, 2].double()) - float(voxel_min[2])) / float(voxel_size)).clamp_(0, gz - 1).long()
+    za, zb = _shard(gz, r, w)
+    mine = (z >= za) & (z < zb)
+    vol = P.voxel_fuse(pts[mine].contiguous(), dirs[mine].contiguous(), dev, grid, voxel_min, voxel_size)
+    dist.all_reduce(vol, op=dist.ReduceOp.SUM)
+    return vol
+
+
+def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
+    """Whole PMVO job with everything resident on the device.  cand float32 [N,3].  -> dict.
+    `mark(name)` (optional) is called at stage boundaries (bench.py records CUDA events there)."""
+    mark = mark or (lambda name: None)
+    mark("start")
+    surface, filt = filter_stage(pm, cand)
+    mark("filter")
+    n_cov = surface.numel()
+    pts = cand[:n_cov][surface].contiguous()
+    fu = cand[:n_cov][filt].contiguous()
+    mark("compact")
+    ori, loss, hc = forward_stage(pm, pts)
+    mark("optimize")
+    o2, l2 = refine_stage(pm, pts, ori, loss)
+    mark("refine")
+    sel = l2 < threshold
+    sp, so = pts[sel].contiguous(), o2[sel].contiguous()
+    dev = pm.device
+    if fu.size(0) > 0 and sp.size(0) >= 100:
+        nbr = knn_stage(sp, fu, 100, dev)
+        fh = pm.filter_head_points(fu, pm.visible_threshold)
+        center = P.medoid_gather(so, nbr, dev)
+        fo, fp = center[~fh], fu[~fh]
+    else:
+        fo, fp = so.new_zeros((0, 3)), so.new_zeros((0, 3))
+    mark("unvisible")
+    vol = fuse_stage(pm, torch.cat([sp, fp], 0), torch.cat([so, fo], 0))
+    mark("fuse")
+    out = {"volume": vol, "surface": surface, "filter": filt, "select_p": pts, "select_o": ori, "min_loss": loss,
+           "high_conf": hc, "refine_o": o2, "refine_loss": l2, "fu_points": fp, "fu_ori": fo,
+           "n_optimized": int(pts.size(0)), "n_selected": int(sp.size(0))}
+    if stats is not None:
+        stats.update(n_candidates=int(cand.size(0)), n_surface=int(pts.size(0)), n_filter=int(fu.size(0)),
+                     n_selected=int(sp.size(0)), n_fu=int(fp.size(0)))
+    return out
+
+
+def pmvo_job_host(camera, depths, Ori, Conf, masks, candidates_host, image_size, patch_size, visible_threshold,
+                  conf_threshold, threshold, device="cuda:0", u8=False):
+    """End to end from HOST buffers to HOST results: H2D of every view's maps (PMVO.__init__), the job, and the
+    D2H read of the fused volume and per-point results."""
+    if u8:
+        pm = P.PMVO.from_u8(camera, depths, Ori, Conf, masks, device=device, image_size=image_size,
+                            patch_size=patch_size, visible_threshold=visible_threshold, conf_threshold=conf_threshold)
+    else:
+        pm = P.PMVO(camera, depths, Ori, Conf, masks, device=device, image_size=image_size, patch_size=patch_size,
+                    visible_threshold=visible_threshold, conf_threshold=conf_threshold)
+    cand = torch.as_tensor(candidates_host).to(device, non_blocking=True).type(torch.float).contiguous()
+    out = pmvo_job_device(pm, cand, threshold)
+    host = {k: out[k].cpu() for k in ("volume", "select_o", "min_loss", "high_conf")}
+    host["n_optimized"] = out["n_optimized"]
+    return host

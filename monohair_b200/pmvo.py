@@ -209,7 +209,7 @@ class PMVO(nn.Module):
         pts = self._pts(points)
         N = pts.size(0)
         dev = self.device
-        sc = scalp_tree.data if hasattr(scalp_tree, "data") else scalp_tree
+        sc = scalp_tree if isinstance(scalp_tree, np.ndarray) or scalp_tree is None else scalp_tree.data
         if sc is None or scalp_max is None:
             raise _lib.MonoHairError("filter_head_points needs the module globals scalp_tree / scalp_max (PMVO.py:99-106)")
         if not hasattr(self, "_scalp") or self._scalp_src is not sc:
