@@ -1,0 +1,59 @@
+"""Drop-in entry point: `python HairGrow.py --yaml=configs/reconstruct/<case>` -- the generate_segments phase of the
+reference's HairGrow.py (:876-919) on monohair_b200's trace kernels; writes scalp_segment.hair and num_root.npy.
+The connect / smooth phases (HairGrow.py:925-976) are "next" rows of SURVEY.md §8f and are not part of this path."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from monohair_b200 import options
+from monohair_b200.hairgrow import HairGrowing, points_to_voxel, save_hair_strands, voxel_to_points  # noqa: F401
+from monohair_b200.pmvo_utils import read_obj, sample_points_uniformly
+
+
+def config_parser():
+    """HairGrow.py:837-873."""
+    opt_cmd = options.parse_arguments(sys.argv[1:])
+    args = options.set(opt_cmd=opt_cmd)
+    args.output_path = os.path.join(args.data.root, args.data.case, args.output_root, args.name)
+    os.makedirs(args.output_path, exist_ok=True)
+    options.save_options_file(args)
+    args.data.root = os.path.join(args.data.root, args.data.case)
+    args.bbox_min = np.array(args.bbox_min)
+    args.bust_to_origin = np.array(args.bust_to_origin)
+    for key in ("strands_path", "bust_path", "scalp_path"):
+        args.data[key] = os.path.join(args.data.root, args.data[key])
+    suffix = '_diffusion' if args.scalp_diffusion else ''
+    args.image_camera_path = os.path.join(args.data.root, args.image_camera_path)
+    args.save_path = os.path.join(args.output_path, 'full' if args.PMVO.infer_inner else 'refine')
+    args.data.Occ3D_path = os.path.join(args.save_path, 'Occ3D{}.mat'.format(suffix))
+    args.data.Ori3D_path = os.path.join(args.save_path, 'Ori3D{}.mat'.format(suffix))
+    return args
+
+
+def main():
+    args = config_parser()
+    v, f = read_obj(args.data.scalp_path)
+    scalp_points, scalp_normals = sample_points_uniformly(v, f, 60000, with_normals=True)
+    scalp_points += args.bust_to_origin
+    scalp_points = torch.from_numpy(scalp_points).to(args.device)
+    scalp_normals = torch.from_numpy(scalp_normals).to(args.device)
+    scalp_normals = scalp_normals / torch.linalg.norm(scalp_normals, 2, -1, keepdims=True)
+    scalp_points = points_to_voxel(scalp_points)
+    scalp_normals[:, 1:] *= -1
+    scalp_normals = scalp_normals.type(torch.float32)
+    scalp_points = scalp_points.type(torch.float32)
+    solver = HairGrowing(args.data.Occ3D_path, args.data.Ori3D_path, device=args.device, image_size=args.data.image_size)
+    if args.HairGenerate.generate_segments:
+        strands, num_root = solver.GenerateGuideStrandFromScalp(scalp_points, scalp_normals, None, args.HairGenerate.grow_threshold)
+        strands = solver.VoxelToWorld(strands, args.bust_to_origin)
+        save_hair_strands(os.path.join(args.save_path, 'scalp_segment.hair'), strands)
+        np.save(args.save_path + '/num_root.npy', np.array(num_root))
+    if args.HairGenerate.connect_segments or args.HairGenerate.connect_scalp:
+        print('connect_segments / connect_scalp are outside the B200 hot path (SURVEY.md §8f); '
+              'run the reference HairGrow.py with --HairGenerate.generate_segments! on the files written here.')
+
+
+if __name__ == '__main__':
+    main()

@@ -212,6 +212,9 @@ def run_b200(args, cfg):
         time.sleep(0.25)
     launches0 = L.mh_launch_count()
     barrier()
+    profiling = os.environ.get("MH_PROFILE") == "1"       # ncu --profile-from-start off: only the timed steps
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStart()
     t_wall0 = time.time()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(torch.cuda.current_stream(dev))
@@ -219,6 +222,8 @@ def run_b200(args, cfg):
         out = one_step(True)
     e_end.record(torch.cuda.current_stream(dev))
     barrier()
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStop()
     t_wall1 = time.time()
     launches = L.mh_launch_count() - launches0
     ms_total = e_start.elapsed_time(e_end)
@@ -334,7 +339,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200":
+        args.warmup = max(args.warmup, int(os.environ.get("MH_BENCH_MIN_WARMUP", "3")))   # profiling runs may lower it
     cfg = WORKLOADS[args.scale]
     if args.impl == "reference":
         run_reference(args, cfg)

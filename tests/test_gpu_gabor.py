@@ -1,0 +1,91 @@
+"""GPU parity of the Gabor kernels: float32 bank against goldens from the unmodified reference (CPU), float64
+calc_orientation_maps path against the numpy/scipy oracle.
+
+Tolerances (float): |responses| 1e-4 relative to the image's max response (289-term fp32 sums in a different order
+than oneDNN's), orientation index exact wherever the top-2 response margin exceeds 1e-4*max (BASELINE.md §3 /
+SURVEY.md §8d config 1), confidence 2e-3 abs on those pixels.  The float64 path is compared at 1e-12.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bank_matches_reference():
+    from monohair_b200.gabor import calOrientationGabor
+    g = load("gabor_small")
+    assert np.array_equal(calOrientationGabor().bank("cuda:0").cpu().numpy(), g["bank"])
+
+
+def test_gabor_orientation_vs_reference_golden():
+    from monohair_b200.gabor import calOrientationGabor
+    from oracle import gabor_oracle as G
+    g = load("gabor_small")
+    img = torch.from_numpy(g["image"])[None, None].cuda()
+    two, orient, conf = calOrientationGabor()(img, None, iter=1, threshold=0.0)
+    orient, conf, two = orient[0, 0].cpu().numpy(), conf[0, 0].cpu().numpy(), two[0].cpu().numpy()
+    _, _, _, res = G.gabor_orientation(g["image"])
+    res = res.numpy()
+    top2 = np.sort(res, axis=0)[-2:]
+    margin = (top2[1] - top2[0]) / res.max()
+    ok = margin > 1e-4
+    print(f"\ngabor: {ok.mean() * 100:.2f}% pixels with top-2 margin > 1e-4; orientation identical on "
+          f"{np.mean(orient == g['orient']) * 100:.3f}% of all pixels")
+    assert ok.mean() > 0.98
+    assert np.array_equal(orient[ok], g["orient"][ok])
+    assert np.abs(conf - g["conf"])[ok].max() <= 2e-3
+    assert np.abs(two - g["two"])[:, ok].max() <= 1e-6
+    # distinct orientation values are exactly the reference's float32 k*pi/180
+    assert set(np.unique(orient)) <= set(np.unique(g["orient"])) | {np.float32(0)}
+
+
+def test_full_frame_properties():
+    """1080p frame: a pure sinusoidal grating must come back with its own orientation (up to the bank's 1 degree),
+    confidence in [0,1], and the result must not depend on the tile decomposition (shifted crop equality)."""
+    from monohair_b200.gabor import calOrientationGabor
+    H, W = 1080, 1920
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    th = math.radians(30.0)
+    img = (0.1 * torch.cos(2 * math.pi * (yy * math.cos(th) + xx * math.sin(th)) / 4.0)).float()
+    m = calOrientationGabor()
+    two, orient, conf = m(img[None, None].cuda())
+    o = orient[0, 0, 100:-100, 100:-100]
+    assert float(conf.min()) >= 0 and float(conf.max()) <= 1
+    assert torch.all((o - th).abs() < math.radians(1.01))
+    crop = img[37:37 + 400, 53:53 + 600].contiguous()
+    _, o2, _ = m(crop[None, None].cuda())
+    assert torch.equal(o2[0, 0, 20:-20, 20:-20], orient[0, 0, 57:417, 73:633])
+
+
+def test_calc_orientation_maps_f64_vs_oracle():
+    from monohair_b200 import gabor as MG
+    from oracle import gabor_oracle as G
+    rng = np.random.default_rng(1)
+    H = W = 96
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.zeros((H, W, 3))
+    for _ in range(30):
+        th, wl = rng.uniform(0, np.pi), rng.uniform(3, 6)
+        img += (np.cos(2 * np.pi * (xx * np.cos(th) + yy * np.sin(th)) / wl) * 20)[..., None]
+    img = np.clip(img + 128 + rng.normal(0, 4, img.shape), 0, 255).astype(np.uint8)
+    ks_o = G.generate_gabor_filters()
+    ks = MG.generate_gabor_filters(1.8, 2.4, 0.23, 180)
+    assert all(np.array_equal(a, b) for a, b in zip(ks, ks_o))
+    F_o = G.calc_orients(img.astype(np.float64), ks_o)
+    F = MG.calc_orients(img.astype(np.float64), ks).cpu().numpy()
+    assert np.abs(F - F_o).max() <= 1e-12 * max(1.0, F_o.max())
+    print(f"\ncalc_orients float64: bit-identical {np.mean(F == F_o) * 100:.2f}%")
+    om_o = F_o.argmax(0)
+    om = F.argmax(0)
+    assert np.mean(om == om_o) > 0.9999
+    V_o = G.calc_confidences(F_o, om_o / 180 * math.pi)
+    V = MG.calc_confidences(torch.from_numpy(F).cuda(), om / 180 * math.pi).cpu().numpy()
+    assert np.allclose(V, V_o, rtol=1e-10, atol=1e-12)
+    d_o = G.difference_of_gaussians(G.rgb2gray(img.astype(np.float64)), 0.4, 10)
+    d = MG.difference_of_gaussians(G.rgb2gray(img.astype(np.float64)), 0.4, 10).cpu().numpy()
+    assert np.abs(d - d_o).max() <= 1e-12
