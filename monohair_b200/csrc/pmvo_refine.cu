@@ -4,6 +4,7 @@
 //   mh_nn_dist            scalp_tree.query(points, k=1) distance (PMVO.py:104)
 //   mh_medoid_gather      compute_points_similarity on gathered neighbours (PMVO_utils.py:366-382)
 #include "mh_common.cuh"
+#include "mh_torch_sum.cuh"
 
 namespace {
 
@@ -338,8 +339,7 @@ medoid_gather_kernel(const float* __restrict__ ori, const int* __restrict__ nbr,
         float best = -1e30f; int bk = 0x7fffffff;
         for (int k = lane; k < K; k += 32) {
             const float a = u[3 * k], b = u[3 * k + 1], c = u[3 * k + 2];
-            float s = 0.0f;
-            for (int j = 0; j < K; ++j) s += fabsf((a * u[3 * j] + b * u[3 * j + 1]) + c * u[3 * j + 2]);
+            float s = mh_torch_inner_sum(K, [&](int j) { return fabsf((a * u[3 * j] + b * u[3 * j + 1]) + c * u[3 * j + 2]); });
             s = s / (float)K;
             if (s > best) { best = s; bk = k; }        // ascending k: first maximum kept
         }

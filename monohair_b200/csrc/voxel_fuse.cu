@@ -12,6 +12,7 @@
 // Bound: HBM streaming.  Algorithmic bytes = n*(12+12) point reads + 4 B/voxel count write+read (x2 for the
 // scan) + 16 B/voxel volume write; 256x256x192: 12.58 M voxels -> 201 MB of volume writes dominate.
 #include "mh_common.cuh"
+#include "mh_torch_sum.cuh"
 
 int mh_exclusive_scan(cudaStream_t st, const int* in, int* out, int64_t n, int* scratch);   // pmvo_refine.cu
 
@@ -56,48 +57,114 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, 
     if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
 }
 
+// Pass 4a: streaming.  Empty voxels -> zeros, single-point voxels -> that point's (flipped) direction,
+// multi-point voxels -> appended to a work list for pass 4b.  Reads 8 B, writes 16 B per voxel, fully coalesced.
 __global__ void __launch_bounds__(256)
-fuse_kernel(int64_t nvox, const int* __restrict__ starts, int* __restrict__ items, const float* __restrict__ dirs,
-            float4* __restrict__ volume) {
+fuse_stream_kernel(int64_t nvox, const int* __restrict__ starts, const int* __restrict__ items,
+                   const float* __restrict__ dirs, float4* __restrict__ volume, int* __restrict__ worklist,
+                   int* __restrict__ wl_count) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nvox) return;
-    const int s = starts[g], e = starts[g + 1];
-    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (e > s) {
-        const int K = e - s;
-        // restore original point order inside the bucket (atomics filled it in arbitrary order)
-        for (int a = s + 1; a < e; ++a) {
-            const int v = items[a];
-            int b = a - 1;
-            while (b >= s && items[b] > v) { items[b + 1] = items[b]; --b; }
-            items[b + 1] = v;
+    bool multi = false;
+    if (g < nvox) {
+        const int s = starts[g], e = starts[g + 1];
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e - s == 1) {
+            float o0, o1, o2;
+            load_dir(dirs, items[s], o0, o1, o2);
+            out = make_float4(o0, -o1, -o2, 1.0f);
         }
-        // medoid under |cos| (compute_points_similarity, PMVO_utils.py:366-382); K == 1 is its own medoid
+        multi = e - s > 1;
+        volume[g] = out;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, multi);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(wl_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (multi) worklist[base + __popc(m & ((1u << lane) - 1))] = (int)g;
+    }
+}
+
+// Pass 4b: one warp per multi-point voxel.  Restores the original point order inside the bucket (the atomics of
+// pass 3 filled it in arbitrary order; argmax ties go to the first point) and takes the medoid under |cos| with
+// torch.mean's summation order (compute_points_similarity, PMVO_utils.py:366-382).
+constexpr int FUSE_WARPS = 4, FUSE_MAXK = 128;
+
+__global__ void __launch_bounds__(FUSE_WARPS * 32)
+fuse_medoid_kernel(const int* __restrict__ worklist, const int* __restrict__ wl_count, const int* __restrict__ starts,
+                   int* __restrict__ items, const float* __restrict__ dirs, float4* __restrict__ volume) {
+    __shared__ int s_idx[FUSE_WARPS][FUSE_MAXK];
+    __shared__ float s_u[FUSE_WARPS][FUSE_MAXK * 3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = *wl_count;
+    for (int w = blockIdx.x * FUSE_WARPS + warp; w < n; w += gridDim.x * FUSE_WARPS) {
+        const int g = worklist[w];
+        const int s = starts[g], K = starts[g + 1] - s;
         int bk = 0;
-        if (K > 1) {
+        if (K <= FUSE_MAXK) {
+            // rank sort by point id
+            for (int a = lane; a < K; a += 32) {
+                const int v = items[s + a];
+                int rank = 0;
+                for (int b = 0; b < K; ++b) rank += (items[s + b] < v) ? 1 : 0;
+                s_idx[warp][rank] = v;
+            }
+            __syncwarp();
+            for (int a = lane; a < K; a += 32) {
+                float a0, a1, a2;
+                load_dir(dirs, s_idx[warp][a], a0, a1, a2);
+                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
+                s_u[warp][3 * a] = a0 / na; s_u[warp][3 * a + 1] = a1 / na; s_u[warp][3 * a + 2] = a2 / na;
+            }
+            __syncwarp();
+            float best = -1e30f; bk = 0x7fffffff;
+            const float* u = s_u[warp];
+            for (int k = lane; k < K; k += 32) {
+                const float a0 = u[3 * k], a1 = u[3 * k + 1], a2 = u[3 * k + 2];
+                float sum = mh_torch_inner_sum(K, [&](int j) { return fabsf((a0 * u[3 * j] + a1 * u[3 * j + 1]) + a2 * u[3 * j + 2]); });
+                sum = sum / (float)K;
+                if (sum > best) { best = sum; bk = k; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+            }
+            if (lane == 0) {
+                float o0, o1, o2;
+                load_dir(dirs, s_idx[warp][bk], o0, o1, o2);
+                volume[g] = make_float4(o0, -o1, -o2, 1.0f);
+            }
+        } else if (lane == 0) {
+            // rare: very crowded voxel, serial path in global memory
+            for (int a = s + 1; a < s + K; ++a) {
+                const int v = items[a];
+                int b = a - 1;
+                while (b >= s && items[b] > v) { items[b + 1] = items[b]; --b; }
+                items[b + 1] = v;
+            }
             float best = -1e30f;
             for (int k = 0; k < K; ++k) {
                 float a0, a1, a2;
                 load_dir(dirs, items[s + k], a0, a1, a2);
                 const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
                 a0 = a0 / na; a1 = a1 / na; a2 = a2 / na;
-                float sum = 0.0f;
-                for (int j = 0; j < K; ++j) {
+                float sum = mh_torch_inner_sum(K, [&](int j) {
                     float b0, b1, b2;
                     load_dir(dirs, items[s + j], b0, b1, b2);
                     const float nb = fmaxf(mh_norm3(b0, b1, b2), 1e-8f);
-                    b0 = b0 / nb; b1 = b1 / nb; b2 = b2 / nb;
-                    sum += fabsf((a0 * b0 + a1 * b1) + a2 * b2);
-                }
+                    return fabsf((a0 * (b0 / nb) + a1 * (b1 / nb)) + a2 * (b2 / nb)); });
                 sum = sum / (float)K;
                 if (sum > best) { best = sum; bk = k; }
             }
+            float o0, o1, o2;
+            load_dir(dirs, items[s + bk], o0, o1, o2);
+            volume[g] = make_float4(o0, -o1, -o2, 1.0f);
         }
-        float o0, o1, o2;
-        load_dir(dirs, items[s + bk], o0, o1, o2);
-        out = make_float4(o0, -o1, -o2, 1.0f);
+        __syncwarp();
     }
-    volume[g] = out;
 }
 
 __global__ void overwrite_kernel(VGrid g, const float* __restrict__ pts, const float* __restrict__ dirs, int64_t n,
@@ -170,10 +237,10 @@ VGrid make_grid(const double* vmin, double vs, int gx, int gy, int gz) {
 
 }  // namespace
 
-// workspace: [counts nvox+1][starts nvox+1][cursor nvox][key n][items n][scan scratch]
+// workspace: [counts nvox+4][starts nvox+4][cursor nvox+4][key n][items n][worklist n/2+4][wl_count 4][scan scratch]
 extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
     const int64_t nvox = (int64_t)gx * gy * gz;
-    return 4 * (3 * (nvox + 4) + 2 * n + nvox / 4096 + 64);
+    return 4 * (3 * (nvox + 4) + 2 * n + (n / 2 + 4) + 4 + nvox / 4096 + 64);
 }
 
 extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
@@ -191,14 +258,24 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
     int* cursor = starts + (nvox + 4);
     int* key = cursor + (nvox + 4);
     int* items = key + n;
-    int* scratch = items + n;
+    int* worklist = items + n;
+    int* wl_count = worklist + (n / 2 + 4);
+    int* scratch = wl_count + 4;
+    cudaMemsetAsync(wl_count, 0, sizeof(int), st);
     cudaMemsetAsync(counts, 0, sizeof(int) * (nvox + 1), st);
     cudaMemsetAsync(cursor, 0, sizeof(int) * nvox, st);
     if (n > 0) { key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, n, key, counts, vox_index); MH_COUNT_LAUNCH(); }
     mh_exclusive_scan(st, counts, starts, nvox, scratch);
     if (n > 0) { fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, starts, cursor, items); MH_COUNT_LAUNCH(); }
-    fuse_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, st>>>(nvox, starts, items, dirs, reinterpret_cast<float4*>(volume));
+    fuse_stream_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, st>>>(nvox, starts, items, dirs, reinterpret_cast<float4*>(volume), worklist, wl_count);
     MH_COUNT_LAUNCH();
+    if (n > 1) {
+        int64_t blocks = (n / 2 + FUSE_WARPS - 1) / FUSE_WARPS;
+        const int64_t cap = (int64_t)mh_sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        fuse_medoid_kernel<<<(unsigned)blocks, FUSE_WARPS * 32, 0, st>>>(worklist, wl_count, starts, items, dirs, reinterpret_cast<float4*>(volume));
+        MH_COUNT_LAUNCH();
+    }
     MH_CHECK_LAUNCH();
     return 0;
 }
