@@ -18,8 +18,13 @@ from . import pmvo as P
 from ._lib import check, lib, ptr, stream_ptr
 
 
+_FORCE_SINGLE = False      # tests: run the single-GPU path inside a multi-rank process
+
+
 def _dist():
     import torch.distributed as dist
+    if _FORCE_SINGLE:
+        return None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist
     return None

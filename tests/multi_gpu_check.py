@@ -1,0 +1,50 @@
+"""Run under torchrun on >= 2 GPUs (not collected by pytest):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
+Checks that the sharded PMVO job (points sharded, volume all-reduce over NCCL) reproduces the single-GPU job
+bit-for-bit: every stage is per-point / per-voxel independent, so sharding must not change a single value."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from monohair_b200 import pipeline, synthetic as syn  # noqa: E402
+from monohair_b200 import pmvo as P  # noqa: E402
+from monohair_b200.camera import cameras_from_scene  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", device_id=dev)
+    sc = syn.make_scene(V=24, H=270, W=480, seed=5)
+    cand = syn.candidate_points(n_cells=6000, num_per_grid=2, seed=5)
+    scalp = syn.scalp_vertices(500, seed=5)
+    P.scalp_tree, P.scalp_max = scalp, scalp.max(0)
+    pm = P.PMVO.from_u8(cameras_from_scene(sc), sc.depth, sc.ori_gray, sc.conf_u8, sc.mask_u8, device=dev,
+                        image_size=[sc.H, sc.W], patch_size=7, visible_threshold=1, conf_threshold=0.15)
+    c = torch.from_numpy(cand).to(dev).float()
+    multi = pipeline.pmvo_job_device(pm, c, 0.025)
+    pipeline._FORCE_SINGLE = True
+    single = pipeline.pmvo_job_device(pm, c, 0.025)
+    pipeline._FORCE_SINGLE = False
+    ok = True
+    for k in ("surface", "filter", "select_o", "min_loss", "high_conf", "refine_o", "refine_loss", "fu_ori", "volume"):
+        same = torch.equal(multi[k], single[k])
+        ok &= same
+        if dist.get_rank() == 0:
+            print(f"{k:12s} identical: {same}")
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if dist.get_rank() == 0:
+        print("MULTI_GPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", "world", dist.get_world_size(),
+              "occupied voxels", int(multi["volume"][..., 3].sum().item()))
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
