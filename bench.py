@@ -168,6 +168,7 @@ def run_b200(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MH_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 

@@ -3,29 +3,30 @@
 //   sample_next_3d_pos (:263-335) -> compute_reproject_ori (:219-241) -> compute_prj_loss (:151-209)
 //   -> per-point best over base views -> normalised direction.
 //
-// One CTA (10 warps) per point at a time, persistent over a work counter.
+// One CTA (OPT_WARPS warps) per point at a time, persistent over a work counter.
 //   A   thread v      : project the point into view v, centre gathers, visibility, Conf'
 //   B   warp0/lane0   : torch.topk order over the views (mh_topk.cuh)          } concurrently
-//   A2  warps 1..9    : stage each VISIBLE view's PxP patch in shared memory   }
+//   A2  other warps   : stage each VISIBLE view's PxP patch in shared memory   }
 //                       as {unit ori, conf}, dropping entries that can never win the reference's scan:
 //                       ineligible ones (conf<=thr in a patch that has some conf>thr, except entry 0) and exact
 //                       duplicates of an earlier kept direction (strict '<' keeps the first) -- both exact.
-//   C   warp b        : base view b; lane = depth sample; loop visible views x staged entries; the [V,N,S]
-//                       tensors of the reference never exist.  View sums follow torch.sum's cascade order.
+//   C   warp w        : base views w, w+OPT_WARPS, ...; each lane owns SPL consecutive depth samples and walks the
+//                       visible views x staged entries with all of them in flight (ILP); the [V,N,S] tensors of
+//                       the reference never exist.  View sums follow torch.sum's cascade order.
 //   D   thread 0      : best base view, direction.
 // Invisible views have weight exactly 0 in the reference (compute_weight, :211-215) so skipping them is exact.
 //
-// Bound: FP32 ALU: ~7 instr per (sample, view, staged entry).  HBM/L2 traffic is only the
-// gathers of phase A/A2: (8 + 16) B per (point, view) + 16 B per (point, visible view, patch entry).
+// Bound: FP32 ALU / issue: ~7 instr per (sample, view, staged entry) + ~70 per (sample, view).
+// HBM/L2 traffic is only the gathers of phase A/A2: (8 + 16) B per (point, view) + 16 B per (point, visible view,
+// patch entry).
 #include "mh_common.cuh"
 #include "mh_topk.cuh"
 
 namespace {
 
-constexpr int OPT_THREADS = 32 * MH_NUM_BASE;
-constexpr int MAX_ROUNDS = 4;                  // S <= 128
-
-struct Ent { float x0, x1, c; };
+constexpr int OPT_WARPS = 5;
+constexpr int OPT_THREADS = 32 * OPT_WARPS;
+constexpr int MAX_SPL = 4;                     // samples per lane: S <= 128
 
 struct Smem {
     MhCam* cams;        // [V]
@@ -40,7 +41,8 @@ struct Smem {
     int* vlist;         // [V] visible views ascending
     MhKV* q;            // [V]
     float* off;         // [S]
-    Ent* ent;           // [V][PP]
+    float2* exy;        // [V][PP] unit patch directions (d_row, d_col)
+    float* ec;          // [V][PP] patch confidences (clamped)
     float* res_loss;    // [NUM_BASE]
     int* res_arg;       // [NUM_BASE]
     int* res_flags;     // [NUM_BASE]  bit0 = high_conf, bit1 = valid
@@ -54,7 +56,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     size_t o_camz = take(4 * V, 4), o_xp = take(4 * V, 4), o_yp = take(4 * V, 4), o_vis = take(4 * V, 4);
     size_t o_orr = take(4 * V, 4), o_orc = take(4 * V, 4), o_pix = take(4 * V, 4), o_ecnt = take(4 * V, 4);
     size_t o_vl = take(4 * V, 4), o_q = take(sizeof(MhKV) * V, 8), o_off = take(4 * S, 4);
-    size_t o_ent = take(sizeof(Ent) * (size_t)V * PP, 4);
+    size_t o_exy = take(sizeof(float2) * (size_t)V * PP, 8), o_ec = take(4 * (size_t)V * PP, 4);
     size_t o_rl = take(4 * MH_NUM_BASE, 4), o_ra = take(4 * MH_NUM_BASE, 4), o_rf = take(4 * MH_NUM_BASE, 4);
     size_t o_misc = take(16, 4);
     if (s) {
@@ -62,7 +64,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
         s->yp = (float*)(base + o_yp); s->vis = (float*)(base + o_vis); s->orr = (float*)(base + o_orr);
         s->orc = (float*)(base + o_orc); s->pix = (int*)(base + o_pix); s->ecnt = (int*)(base + o_ecnt);
         s->vlist = (int*)(base + o_vl); s->q = (MhKV*)(base + o_q); s->off = (float*)(base + o_off);
-        s->ent = (Ent*)(base + o_ent); s->res_loss = (float*)(base + o_rl); s->res_arg = (int*)(base + o_ra);
+        s->exy = (float2*)(base + o_exy); s->ec = (float*)(base + o_ec);
+        s->res_loss = (float*)(base + o_rl); s->res_arg = (int*)(base + o_ra);
         s->res_flags = (int*)(base + o_rf); s->misc = (int*)(base + o_misc);
     }
     return o;
@@ -95,18 +98,107 @@ MH_D bool arg_better(float av, int ai, float bv, int bi) {
     return av < bv || (av == bv && ai < bi);
 }
 
-// loss of one (sample, view): scan of the staged entries (compute_prj_loss :164-182)
-MH_D void scan_entries(const Ent* __restrict__ e, int cnt, float y0, float y1, float& best_l, float& best_c) {
-    Ent t = e[0];
-    best_l = 1.0f - fabsf(t.x0 * y0 + t.x1 * y1);
-    best_c = t.c;
-    for (int k = 1; k < cnt; ++k) {
-        t = e[k];
-        const float l = 1.0f - fabsf(t.x0 * y0 + t.x1 * y1);
-        if (l < best_l) { best_l = l; best_c = t.c; }
+// One base view handled by one warp: compute_prj_loss (:151-209) for its S samples.
+template <int SPL, typename Cascade>
+MH_D void process_base(const Smem& sm, const mh_views& vw, int b, int S, int PP, float thr_c, int lane) {
+    const int V = vw.V;
+    const float Wf = (float)vw.W, Hf = (float)vw.H;
+    const int bview = sm.q[2 * b].i;
+    const float bval = sm.q[2 * b].v;
+    const bool valid = (b == 0) || (bval > 0.0f);                                     // :57-64
+    if (!valid) {                                                                      // warp-uniform
+        if (lane == 0) { sm.res_loss[b] = 0.0f; sm.res_arg[b] = 0; sm.res_flags[b] = 0; }
+        return;
+    }
+    const int nvis = sm.misc[0];
+    float wx[SPL], wy[SPL], wz[SPL];
+    int cnt[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = min(lane * SPL + j, S - 1);
+        sample_point(sm, bview, sm.off[s], Wf, Hf, wx[j], wy[j], wz[j]);
+        cnt[j] = 0;
+    }
+    Cascade acc;                                                                       // channels: 2j = sum l*w, 2j+1 = sum w
+    acc.init(V);
+    for (int jv = 0; jv < nvis; ++jv) {
+        const int v = sm.vlist[jv];
+        const MhCam& cm = sm.cams[v];
+        const float ypv = sm.yp[v], xpv = sm.xp[v];
+        float y0[SPL], y1[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            float cx, cy, cz, xs, ys;
+            mh_world_to_cam(cm.p, wx[j], wy[j], wz[j], cx, cy, cz);
+            mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, cx, cy, cz, xs, ys);
+            mh_normalize2(ys - ypv, xs - xpv, y0[j], y1[j]);                           // (d_row, d_col) :237
+        }
+        // scan of the staged entries (:164-182): entry 0 seeds, later entries replace on strict '<'
+        const float2* __restrict__ exy = sm.exy + (size_t)v * PP;
+        const int ne = sm.ecnt[v];
+        float bl[SPL];
+        int bk[SPL];
+        {
+            const float2 x = exy[0];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) { bl[j] = 1.0f - fabsf(x.x * y0[j] + x.y * y1[j]); bk[j] = 0; }
+        }
+#pragma unroll 4
+        for (int k = 1; k < ne; ++k) {
+            const float2 x = exy[k];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const float l = 1.0f - fabsf(x.x * y0[j] + x.y * y1[j]);
+                if (l < bl[j]) { bl[j] = l; bk[j] = k; }
+            }
+        }
+        const float* __restrict__ ec = sm.ec + (size_t)v * PP;
+        acc.begin_row(v);
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const float c = ec[bk[j]];
+            acc.add(2 * j, bl[j] * c);                                                 // min_loss * weight :195
+            acc.add(2 * j + 1, c);
+            cnt[j] += (c > 0.0f) ? 1 : 0;
+        }
+    }
+    float sums[2 * SPL];
+    acc.finish(V, sums);
+    float Lraw[SPL];
+    bool pos[SPL];
+    int npos = 0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const bool act = lane * SPL + j < S;
+        pos[j] = act && ((sums[2 * j + 1] / (float)cnt[j]) > thr_c);                   // :198
+        Lraw[j] = sums[2 * j] / sums[2 * j + 1];                                       // :201
+        npos += __popc(__ballot_sync(0xffffffffu, pos[j]));
+    }
+    const bool low = npos < 5;                                                          // :199
+    float bestv = 0.0f; int besti = 0x7fffffff; bool bestpos = false;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        if (s < S) {
+            const float L = (low || pos[j]) ? Lraw[j] : 1.0f;                          // :203-204
+            if (besti == 0x7fffffff || arg_better(L, s, bestv, besti)) { bestv = L; besti = s; bestpos = pos[j]; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        const int op = __shfl_xor_sync(0xffffffffu, (int)bestpos, o);
+        if (oi != 0x7fffffff && (besti == 0x7fffffff || arg_better(ov, oi, bestv, besti))) { bestv = ov; besti = oi; bestpos = op != 0; }
+    }
+    if (lane == 0) {
+        sm.res_loss[b] = bestv;
+        sm.res_arg[b] = besti;
+        sm.res_flags[b] = (bestpos ? 1 : 0) | 2;
     }
 }
 
+template <int SPL, bool BIGV>
 __global__ void __launch_bounds__(OPT_THREADS)
 optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const float* __restrict__ offsets, int S,
                 float thr_c, float* __restrict__ out_ori, float* __restrict__ out_loss,
@@ -170,40 +262,45 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
                 }
                 if (lane == 0) sm.misc[0] = cnt;
             }
-            for (int v = warp - 1; v < V; v += MH_NUM_BASE - 1) {
+            for (int v = warp - 1; v < V; v += OPT_WARPS - 1) {
                 if (sm.vis[v] == -1.0f) { if (lane == 0) sm.ecnt[v] = 0; continue; }
                 const int pix = sm.pix[v];
                 const int row = pix / vw.W, col = pix - row * vw.W;
                 const float4* __restrict__ mp = mapP + (size_t)v * plane;
                 const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mp + pix) + 3), 1e-6f), 1.0f);
                 const bool hi = cmax > thr_c;                                        // :162
-                Ent* seg = sm.ent + (size_t)v * PP;
+                float2* sxy = sm.exy + (size_t)v * PP;
+                float* sc = sm.ec + (size_t)v * PP;
                 int kept = 0;
                 for (int p0 = 0; p0 < PP; p0 += 32) {
                     const int p = p0 + lane;
-                    Ent e; e.x0 = e.x1 = e.c = 0.0f;
+                    float ex0 = 0.0f, ex1 = 0.0f, ecf = 0.0f;
                     bool elig = false;
                     if (p < PP) {
                         const int di = p / P - half, dj = p % P - half;                 // row offset outer (:494-500)
                         const int r = min(max(row + di, 0), vw.H - 1), c = min(max(col + dj, 0), vw.W - 1);
                         const float4 t = __ldg(mp + (size_t)r * vw.W + c);
-                        mh_normalize2(t.x, t.y, e.x0, e.x1);
-                        e.c = fminf(fmaxf(t.z, 1e-6f), 1.0f);
-                        elig = (p == 0) || !hi || (e.c > thr_c);
+                        mh_normalize2(t.x, t.y, ex0, ex1);
+                        ecf = fminf(fmaxf(t.z, 1e-6f), 1.0f);
+                        elig = (p == 0) || !hi || (ecf > thr_c);
                         // duplicate of an entry already kept in an earlier 32-chunk?
-                        if (elig) for (int k = 0; k < kept; ++k) if (seg[k].x0 == e.x0 && seg[k].x1 == e.x1) { elig = false; break; }
+                        if (elig) for (int k = 0; k < kept; ++k) if (sxy[k].x == ex0 && sxy[k].y == ex1) { elig = false; break; }
                     }
                     // duplicate of an earlier eligible lane in this chunk?
                     bool dup = false;
                     for (int l2 = 0; l2 < 31; ++l2) {
-                        const float ox0 = __shfl_sync(0xffffffffu, e.x0, l2), ox1 = __shfl_sync(0xffffffffu, e.x1, l2);
+                        const float ox0 = __shfl_sync(0xffffffffu, ex0, l2), ox1 = __shfl_sync(0xffffffffu, ex1, l2);
                         const bool oel = __shfl_sync(0xffffffffu, (int)elig, l2) != 0;
-                        if (l2 < lane && oel && ox0 == e.x0 && ox1 == e.x1) dup = true;
+                        if (l2 < lane && oel && ox0 == ex0 && ox1 == ex1) dup = true;
                     }
                     const bool keep = elig && !dup;
                     const unsigned m = __ballot_sync(0xffffffffu, keep);
                     __syncwarp();
-                    if (keep) seg[kept + __popc(m & ((1u << lane) - 1))] = e;
+                    if (keep) {
+                        const int slot = kept + __popc(m & ((1u << lane) - 1));
+                        sxy[slot] = make_float2(ex0, ex1);
+                        sc[slot] = ecf;
+                    }
                     kept += __popc(m);
                     __syncwarp();
                 }
@@ -212,76 +309,10 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
         }
         __syncthreads();
 
-        // ---- C: warp b = base view b ----
-        {
-            const int b = warp;
-            const int bview = sm.q[2 * b].i;
-            const float bval = sm.q[2 * b].v;
-            const bool valid = (b == 0) || (bval > 0.0f);                             // :57-64
-            float Lraw[MAX_ROUNDS];
-            unsigned posbits = 0;
-            const int nvis = sm.misc[0];
-            const int rounds = (S + 31) >> 5;
-            if (valid) {
-#pragma unroll
-                for (int r = 0; r < MAX_ROUNDS; ++r) {
-                    Lraw[r] = 0.0f;
-                    if (r >= rounds) continue;
-                    const int s = r * 32 + lane;
-                    if (s >= S) continue;
-                    float wx, wy, wz;
-                    sample_point(sm, bview, sm.off[s], Wf, Hf, wx, wy, wz);
-                    MhCascade<2> acc;
-                    acc.init(V);
-                    int cnt = 0;
-                    for (int j = 0; j < nvis; ++j) {
-                        const int v = sm.vlist[j];
-                        const MhCam& cm = sm.cams[v];
-                        float cx, cy, cz, xs, ys;
-                        mh_world_to_cam(cm.p, wx, wy, wz, cx, cy, cz);
-                        mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, cx, cy, cz, xs, ys);
-                        float y0, y1;
-                        mh_normalize2(ys - sm.yp[v], xs - sm.xp[v], y0, y1);           // (d_row, d_col) :237
-                        float bl, bc;
-                        scan_entries(sm.ent + (size_t)v * PP, sm.ecnt[v], y0, y1, bl, bc);
-                        acc.begin_row(v);
-                        acc.add(0, bl * bc);                                           // min_loss * weight :195
-                        acc.add(1, bc);
-                        cnt += (bc > 0.0f) ? 1 : 0;
-                    }
-                    float sums[2];
-                    acc.finish(V, sums);
-                    const bool pos = (sums[1] / (float)cnt) > thr_c;                    // :198
-                    Lraw[r] = sums[0] / sums[1];                                        // :201
-                    if (pos) posbits |= 1u << r;
-                }
-            }
-            int npos = 0;
-#pragma unroll
-            for (int r = 0; r < MAX_ROUNDS; ++r) npos += __popc(__ballot_sync(0xffffffffu, (posbits >> r) & 1u));
-            const bool low = npos < 5;                                                  // :199
-            float bestv = 0.0f; int besti = 0x7fffffff; bool bestpos = false;
-#pragma unroll
-            for (int r = 0; r < MAX_ROUNDS; ++r) {
-                const int s = r * 32 + lane;
-                if (r < rounds && s < S) {
-                    const bool pos = (posbits >> r) & 1u;
-                    const float L = (low || pos) ? Lraw[r] : 1.0f;                      // :203-204
-                    if (besti == 0x7fffffff || arg_better(L, s, bestv, besti)) { bestv = L; besti = s; bestpos = pos; }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-                const int op = __shfl_xor_sync(0xffffffffu, (int)bestpos, o);
-                if (oi != 0x7fffffff && (besti == 0x7fffffff || arg_better(ov, oi, bestv, besti))) { bestv = ov; besti = oi; bestpos = op != 0; }
-            }
-            if (lane == 0) {
-                sm.res_loss[b] = bestv;
-                sm.res_arg[b] = besti;
-                sm.res_flags[b] = (bestpos ? 1 : 0) | (valid ? 2 : 0);
-            }
+        // ---- C: base views, one warp each ----
+        for (int b = warp; b < MH_NUM_BASE; b += OPT_WARPS) {
+            if (BIGV) process_base<SPL, MhCascade<2 * SPL>>(sm, vw, b, S, PP, thr_c, lane);
+            else process_base<SPL, MhCascadeSmall<2 * SPL>>(sm, vw, b, S, PP, thr_c, lane);
         }
         __syncthreads();
 
@@ -312,6 +343,20 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
     }
 }
 
+typedef void (*OptKernel)(mh_views, const float*, int64_t, const float*, int, float, float*, float*, uint8_t*, int32_t*,
+                          float*, float*, float*, int32_t*, unsigned long long*);
+
+OptKernel pick_kernel(int S, int V) {
+    const int spl = (S + 31) / 32;
+    const bool big = V >= 256;
+    switch (spl) {
+        case 1: return big ? optimize_kernel<1, true> : optimize_kernel<1, false>;
+        case 2: return big ? optimize_kernel<2, true> : optimize_kernel<2, false>;
+        case 3: return big ? optimize_kernel<3, true> : optimize_kernel<3, false>;
+        default: return big ? optimize_kernel<4, true> : optimize_kernel<4, false>;
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t mh_pmvo_optimize_workspace_bytes(const mh_views* views, int64_t N) {
@@ -329,11 +374,10 @@ extern "C" int mh_pmvo_optimize(void* stream, const mh_views* vw, const float* p
     MH_CHECK_ARG(points && offsets && ori && loss && high_conf && workspace && N > 0, "null pointer");
     MH_CHECK_ARG(workspace_bytes >= 256, "workspace too small");
     MH_CHECK_ARG(vw->V >= MH_TOPK, "PMVO.forward needs at least 20 views (torch.topk(...,20), PMVO.py:341)");
-    MH_CHECK_ARG(S >= 1 && S <= 32 * MAX_ROUNDS, "num_sample must be in [1,128]");
+    MH_CHECK_ARG(S >= 1 && S <= 32 * MAX_SPL, "num_sample must be in [1,128]");
     MH_CHECK_ARG((vw->P & 1) && vw->P >= 1, "patch size must be odd");
     MH_CHECK_ARG((dbg_base_idx == nullptr) == (dbg_base_val == nullptr), "dbg_base_idx/val must come together");
     MH_CHECK_ARG((dbg_loss_b == nullptr) == (dbg_arg_b == nullptr), "dbg_loss_b/arg_b must come together");
-    if (N == 0) return 0;
     const size_t smem = smem_layout(nullptr, nullptr, vw->V, S, vw->P * vw->P);
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
@@ -343,15 +387,16 @@ extern "C" int mh_pmvo_optimize(void* stream, const mh_views* vw, const float* p
                      vw->V * vw->P * vw->P, smem, max_smem);
         return 1;
     }
-    cudaError_t e = cudaFuncSetAttribute(optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    OptKernel kern = pick_kernel(S, vw->V);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { mh_set_error("mh_pmvo_optimize: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 2; }
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, optimize_kernel, OPT_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OPT_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)mh_sm_count() * per_sm;
     if (grid > N) grid = N;
     cudaMemsetAsync(workspace, 0, 8, (cudaStream_t)stream);
-    optimize_kernel<<<(unsigned)grid, OPT_THREADS, smem, (cudaStream_t)stream>>>(
+    kern<<<(unsigned)grid, OPT_THREADS, smem, (cudaStream_t)stream>>>(
         *vw, points, N, offsets, S, conf_threshold, ori, loss, high_conf, dbg_base_idx, dbg_base_val,
         dbg_best_sample, dbg_loss_b, dbg_arg_b, reinterpret_cast<unsigned long long*>(workspace));
     MH_COUNT_LAUNCH();

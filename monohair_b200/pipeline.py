@@ -92,15 +92,30 @@ def knn_stage(ref, query, k, dev):
     return _all_gather_rows(idx, n, w, dist)
 
 
+def head_filter_stage(pm, pts, thr):
+    """PMVO.filter_head_points for all points at once (it depends on positions only), sharded over ranks."""
+    dist = _dist()
+    if dist is None or pts.size(0) == 0:
+        return pm.filter_head_points(pts, thr)
+    r, w = dist.get_rank(), dist.get_world_size()
+    n = pts.size(0)
+    a, b = _shard(n, r, w)
+    f = pm.filter_head_points(pts[a:b].contiguous(), thr).to(torch.uint8)
+    return _all_gather_rows(f, n, w, dist).bool()
+
+
 def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
-    """PMVO.refine step (i): sharded kNN, then the chunk-sequential medoid / re-score / update (replicated: it is
-    Gauss-Seidel across chunks, §9-R7, and tiny next to forward)."""
+    """PMVO.refine step (i).  Position-only work is hoisted out of the chunk loop and sharded over ranks: the kNN
+    and the head filter.  What remains sequential is what the reference makes sequential: medoid of the CURRENT
+    neighbour orientations -> re-score -> in-place update, chunk by chunk (Gauss-Seidel across chunks, §9-R7);
+    it is replicated on every rank (each needs the final arrays)."""
     dev = pm.device
     n = pts.size(0)
     o, l = ori.clone(), loss.clone()
     if n == 0:
         return o, l
     nbr = knn_stage(pts, pts, k, dev)
+    filt = head_filter_stage(pm, pts, pm.visible_threshold).to(torch.uint8).contiguous()
     with torch.cuda.device(dev):
         st = stream_ptr(dev)
         for i in range(n // sub_num + 1):
@@ -109,8 +124,7 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
                 continue
             center = P.medoid_gather(o, nbr[a:b], dev)
             upd = pm.refine_loss_raw(pts[a:b], center)
-            filt = pm.filter_head_points(pts[a:b], pm.visible_threshold)
-            check(lib().mh_refine_update(st, ptr(center), ptr(upd), ptr(filt.to(torch.uint8)), b - a, ptr(o[a:b]), ptr(l[a:b])),
+            check(lib().mh_refine_update(st, ptr(center), ptr(upd), ptr(filt[a:b]), b - a, ptr(o[a:b]), ptr(l[a:b])),
                   "mh_refine_update")
     return o, l
 
@@ -153,7 +167,7 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
     dev = pm.device
     if fu.size(0) > 0 and sp.size(0) >= 100:
         nbr = knn_stage(sp, fu, 100, dev)
-        fh = pm.filter_head_points(fu, pm.visible_threshold)
+        fh = head_filter_stage(pm, fu, pm.visible_threshold)
         center = P.medoid_gather(so, nbr, dev)
         fo, fp = center[~fh], fu[~fh]
     else:

@@ -372,21 +372,8 @@ def refine_points(points, ori, loss, pmvo, sub_num=5000, k=100):
     pts = torch.as_tensor(points).to(dev).type(torch.float).contiguous()
     o = torch.as_tensor(ori).to(dev).type(torch.float).contiguous().clone()
     l = torch.as_tensor(loss).to(dev).type(torch.float).contiguous().clone()
-    n = pts.size(0)
-    if n == 0:
-        return pts, o, l
-    nbr = knn(pts, pts, k, dev)
-    with torch.cuda.device(dev):
-        st = stream_ptr(dev)
-        for i in range(n // sub_num + 1):
-            a, b = i * sub_num, min((i + 1) * sub_num, n)
-            if b <= a:
-                continue
-            center = medoid_gather(o, nbr[a:b], dev)
-            upd = pmvo.refine_loss_raw(pts[a:b], center)
-            filt = pmvo.filter_head_points(pts[a:b], pmvo.visible_threshold)
-            check(lib().mh_refine_update(st, ptr(center), ptr(upd), ptr(filt.to(torch.uint8)), b - a, ptr(o[a:b]), ptr(l[a:b])),
-                  "mh_refine_update")
+    from . import pipeline
+    o, l = pipeline.refine_stage(pmvo, pts, o, l, sub_num=sub_num, k=k)
     return pts, o, l
 
 
