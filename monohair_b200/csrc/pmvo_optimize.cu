@@ -26,6 +26,9 @@ namespace {
 
 constexpr int OPT_WARPS = 5;
 constexpr int OPT_THREADS = 32 * OPT_WARPS;
+#ifndef OPT_MIN_BLOCKS
+#define OPT_MIN_BLOCKS 4
+#endif
 constexpr int MAX_SPL = 4;                     // samples per lane: S <= 128
 
 struct Smem {
@@ -199,7 +202,7 @@ MH_D void process_base(const Smem& sm, const mh_views& vw, int b, int S, int PP,
 }
 
 template <int SPL, bool BIGV>
-__global__ void __launch_bounds__(OPT_THREADS)
+__global__ void __launch_bounds__(OPT_THREADS, OPT_MIN_BLOCKS)
 optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const float* __restrict__ offsets, int S,
                 float thr_c, float* __restrict__ out_ori, float* __restrict__ out_loss,
                 uint8_t* __restrict__ out_hc, int32_t* __restrict__ dbg_bidx, float* __restrict__ dbg_bval,

@@ -215,12 +215,14 @@ __device__ void warp_sort256(Cand* buf, int lane) {
 
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_query_kernel(Grid g, const float* __restrict__ ref, const int* __restrict__ starts, const int* __restrict__ items,
-                 const float* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx) {
+                 const float* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx,
+                 const unsigned char* __restrict__ only_flagged) {
     __shared__ Cand bufs[KNN_WARPS][KNN_BUF];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Cand* buf = bufs[warp];
     const double INF = 1e300;
     for (int64_t q = (int64_t)blockIdx.x * KNN_WARPS + warp; q < nq; q += (int64_t)gridDim.x * KNN_WARPS) {
+        if (only_flagged && !only_flagged[q]) continue;
         const double qx = query[3 * q], qy = query[3 * q + 1], qz = query[3 * q + 2];
         const int cx = cell_of(qx, g.ox, g.h, g.nx), cy = cell_of(qy, g.oy, g.h, g.ny), cz = cell_of(qz, g.oz, g.h, g.nz);
         for (int t = lane; t < KNN_BUF; t += 32) { buf[t].d = INF; buf[t].i = 0x7fffffff; }
@@ -295,6 +297,145 @@ knn_query_kernel(Grid g, const float* __restrict__ ref, const int* __restrict__ 
             if (margin > 0 && bound < margin * margin) break;
         }
         for (int t = lane; t < K; t += 32) out_idx[q * K + t] = buf[t].i;
+        __syncwarp();
+    }
+}
+
+
+// ---- fast path: gather ring candidates once, pick a radius by bisection, sort <= 256 survivors once ----------
+// The cell size is ~ the k-NN radius, so rings 0..1 usually hold all k neighbours.  Candidates (squared float64
+// distance, index) of the visited rings are kept in shared memory (KF_CAP per warp).  A bisection on the squared
+// radius finds U >= d_k with at most 256 candidates inside; survivors are compacted, and the search ends when the
+// visited block contains the ball of radius sqrt(U).  One bitonic sort orders the survivors by (distance, index).
+// Queries that overflow the buffer or cannot be separated (hundreds of equidistant points) are flagged and redone
+// by the general kernel above.
+constexpr int KF_WARPS = 4, KF_CAP = 768, KF_SORT = 256;
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(KF_WARPS * 32)
+knn_query_fast_kernel(Grid g, const float* __restrict__ ref, const int* __restrict__ starts, const int* __restrict__ items,
+                      const float* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx,
+                      unsigned char* __restrict__ flags) {
+    __shared__ double sd_all[KF_WARPS][KF_CAP];
+    __shared__ int si_all[KF_WARPS][KF_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sd = sd_all[warp];
+    int* si = si_all[warp];
+    const double INF = 1e300;
+    for (int64_t q = (int64_t)blockIdx.x * KF_WARPS + warp; q < nq; q += (int64_t)gridDim.x * KF_WARPS) {
+        const double qx = query[3 * q], qy = query[3 * q + 1], qz = query[3 * q + 2];
+        const int cx = cell_of(qx, g.ox, g.h, g.nx), cy = cell_of(qy, g.oy, g.h, g.ny), cz = cell_of(qz, g.oz, g.h, g.nz);
+        const int maxR = max(max(max(cx, g.nx - 1 - cx), max(cy, g.ny - 1 - cy)), max(cz, g.nz - 1 - cz));
+        int nc = 0;
+        double U = INF;
+        bool fail = false, done = false;
+        for (int R = 0; R <= maxR && !fail && !done; ++R) {
+            const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
+            const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+            const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
+            for (int z = z0; z <= z1 && !fail; ++z)
+                for (int y = y0; y <= y1 && !fail; ++y) {
+                    const bool edge_zy = (abs(z - cz) == R) || (abs(y - cy) == R);
+                    for (int seg = 0; seg < (edge_zy ? 1 : 2) && !fail; ++seg) {
+                        int xa, xb;
+                        if (edge_zy) { xa = x0; xb = x1; }
+                        else {
+                            const int xx = seg == 0 ? cx - R : cx + R;
+                            if (xx < 0 || xx >= g.nx || (seg == 1 && R == 0)) continue;
+                            xa = xb = xx;
+                        }
+                        const int rowc = (z * g.ny + y) * g.nx;
+                        const int s = starts[rowc + xa], e = starts[rowc + xb + 1];
+                        for (int it0 = s; it0 < e; it0 += 32) {
+                            const int it = it0 + lane;
+                            bool ok = false;
+                            double d = INF; int ri = 0;
+                            if (it < e) {
+                                ri = items[it];
+                                const double dx = qx - (double)ref[3 * ri], dy = qy - (double)ref[3 * ri + 1], dz = qz - (double)ref[3 * ri + 2];
+                                d = dx * dx + dy * dy + dz * dz;
+                                ok = d <= U;
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, ok);
+                            if (nc + __popc(m) > KF_CAP) { fail = true; break; }
+                            if (ok) { const int slot = nc + __popc(m & ((1u << lane) - 1)); sd[slot] = d; si[slot] = ri; }
+                            nc += __popc(m);
+                        }
+                    }
+                }
+            if (fail) break;
+            if ((R == 0 && maxR > 0) || nc < K) continue;
+            __syncwarp();
+            // bisection for U: count(d <= U) in [K, KF_SORT]
+            double hi = 0.0;
+            for (int t = lane; t < nc; t += 32) hi = fmax(hi, sd[t]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            int chi = nc;
+            double lo = 0.0;
+            for (int iter = 0; iter < 60 && chi > KF_SORT; ++iter) {
+                const double mid = 0.5 * (lo + hi);
+                int c = 0;
+                for (int t = lane; t < nc; t += 32) c += (sd[t] <= mid) ? 1 : 0;
+                c = warp_sum(c);
+                if (c >= K) { hi = mid; chi = c; } else lo = mid;
+            }
+            if (chi > KF_SORT) { fail = true; break; }
+            U = hi;
+            // compact survivors in place
+            if (chi < nc) {
+                int base = 0;
+                for (int t0 = 0; t0 < nc; t0 += 32) {
+                    const int t = t0 + lane;
+                    double d = INF; int ri = 0;
+                    if (t < nc) { d = sd[t]; ri = si[t]; }
+                    const bool keep = t < nc && d <= U;
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    __syncwarp();
+                    if (keep) { const int slot = base + __popc(m & ((1u << lane) - 1)); sd[slot] = d; si[slot] = ri; }
+                    base += __popc(m);
+                    __syncwarp();
+                }
+                nc = base;
+            }
+            double margin = INF;
+            if (cx - R > 0) margin = fmin(margin, qx - (g.ox + (double)(cx - R) * g.h));
+            if (cx + R < g.nx - 1) margin = fmin(margin, (g.ox + (double)(cx + R + 1) * g.h) - qx);
+            if (cy - R > 0) margin = fmin(margin, qy - (g.oy + (double)(cy - R) * g.h));
+            if (cy + R < g.ny - 1) margin = fmin(margin, (g.oy + (double)(cy + R + 1) * g.h) - qy);
+            if (cz - R > 0) margin = fmin(margin, qz - (g.oz + (double)(cz - R) * g.h));
+            if (cz + R < g.nz - 1) margin = fmin(margin, (g.oz + (double)(cz + R + 1) * g.h) - qz);
+            if (margin > 0 && U < margin * margin) done = true;
+        }
+        if (fail || !done || nc < K || nc > KF_SORT) {
+            if (lane == 0) flags[q] = 1;
+            __syncwarp();
+            continue;
+        }
+        // one bitonic sort of the survivors by (distance, index), padded to a power of two
+        const int n2 = nc <= 128 ? 128 : 256;
+        for (int t = nc + lane; t < n2; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
+        __syncwarp();
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < n2 / 2; t += 32) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int p = i | j;
+                    const bool up = (i & k) == 0;
+                    const double da = sd[i], db = sd[p];
+                    const int ia = si[i], ib = si[p];
+                    const bool b_lt_a = db < da || (db == da && ib < ia);
+                    if (b_lt_a == up) { sd[i] = db; sd[p] = da; si[i] = ib; si[p] = ia; }
+                }
+                __syncwarp();
+            }
+        for (int t = lane; t < K; t += 32) out_idx[q * K + t] = si[t];
+        if (lane == 0) flags[q] = 0;
         __syncwarp();
     }
 }
@@ -382,7 +523,7 @@ static const int64_t KNN_MAX_CELLS = 1ll << 24;
 
 extern "C" int64_t mh_knn_workspace_bytes(int64_t n_ref, int64_t n_query, int32_t k) {
     (void)n_query; (void)k;
-    return 256 + 4 * (3 * (KNN_MAX_CELLS + 2) + 2 * n_ref + KNN_MAX_CELLS / 4096 + 16);
+    return 256 + 4 * (3 * (KNN_MAX_CELLS + 2) + 2 * n_ref + KNN_MAX_CELLS / 4096 + 16) + ((n_query + 15) / 16) * 16;
 }
 
 extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float* query, int64_t n_query, int32_t k,
@@ -411,6 +552,7 @@ extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float
     int* cell_of_pt = cursor + (KNN_MAX_CELLS + 2);
     int* items = cell_of_pt + n_ref;
     int* scratch = items + n_ref;
+    unsigned char* flags = reinterpret_cast<unsigned char*>(scratch + (KNN_MAX_CELLS / 4096 + 16));
     cudaMemsetAsync(counts, 0, sizeof(int) * (ncell + 1), st);
     cudaMemsetAsync(cursor, 0, sizeof(int) * ncell, st);
     knn_count_kernel<<<(unsigned)((n_ref + 255) / 256), 256, 0, st>>>(g, ref, n_ref, counts, cell_of_pt);
@@ -421,7 +563,9 @@ extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float
     int64_t blocks = (n_query + KNN_WARPS - 1) / KNN_WARPS;
     const int64_t cap = (int64_t)mh_sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    knn_query_kernel<<<(unsigned)blocks, KNN_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx);
+    knn_query_fast_kernel<<<(unsigned)blocks, KF_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx, flags);
+    MH_COUNT_LAUNCH();
+    knn_query_kernel<<<(unsigned)blocks, KNN_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx, flags);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;

@@ -314,10 +314,19 @@ def optimize(points, pmvo, args, chunk=1 << 20):
 def knn(ref, query, k, dev):
     """Exact kNN (float64 distances) of `query` [n,3] among `ref` [m,3], both float32 device tensors."""
     m, n = ref.size(0), query.size(0)
-    lo, hi = ref.amin(0).double().cpu().numpy(), ref.amax(0).double().cpu().numpy()
+    lo_t, hi_t = ref.amin(0), ref.amax(0)
+    lo, hi = lo_t.double().cpu().numpy(), hi_t.double().cpu().numpy()
     ext = np.maximum(hi - lo, 1e-9)
-    # cell size: ~k/4 points per cell if the points filled the box; surface-like clouds put more in each occupied cell
-    cell = float(max((ext.prod() * max(k, 8) / 4.0 / max(m, 1)) ** (1.0 / 3.0), ext.max() / 1000.0))
+    # Cell size ~ the k-NN radius.  The clouds here are thin shells, so the density is estimated from the cells that
+    # are actually occupied at a probe resolution (not from the bounding box): rho = m / (occupied cells * h0^3),
+    # r_k = (3k / (4 pi rho))^(1/3).  Too small only costs more shells, too large more candidates; both stay exact.
+    h0 = float(max(ext.max() / 128.0, 1e-6))
+    sub = ref[:: max(1, m // 200000)]
+    cid = ((sub - lo_t) / h0).floor().long()
+    ncell = torch.unique(cid[:, 0] * (1 << 40) + cid[:, 1] * (1 << 20) + cid[:, 2]).numel()
+    rho = m / max(ncell * h0 ** 3, 1e-30)
+    r_k = (3.0 * k / (4.0 * math.pi * rho)) ** (1.0 / 3.0)
+    cell = float(min(max(1.15 * r_k, ext.max() / 1000.0), ext.max()))
     bbox = np.concatenate([lo, hi]).astype(np.float64)
     idx = torch.empty((n, k), dtype=torch.int32, device=dev)
     wsb = lib().mh_knn_workspace_bytes(m, n, k)

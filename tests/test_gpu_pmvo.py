@@ -200,6 +200,23 @@ def test_knn_exact_vs_kdtree():
     assert np.mean(idx == i_ref) > 0.9999
 
 
+def test_knn_fallback_paths():
+    """dense clumps (buffer overflow) and hundreds of coincident points (no separating radius) take the general
+    kernel; results must still be the exact k nearest by distance."""
+    from monohair_b200 import pmvo as P
+    rng = np.random.default_rng(3)
+    base = rng.uniform(-0.1, 0.1, (4000, 3)).astype(np.float32)
+    clump = (np.array([[0.01, 0.02, 0.03]], np.float32) + rng.normal(0, 1e-5, (3000, 3))).astype(np.float32)
+    dup = np.repeat(np.array([[-0.05, 0.0, 0.05]], np.float32), 400, axis=0)
+    ref = np.concatenate([base, clump, dup])
+    q = np.concatenate([ref[::7], np.array([[0.01, 0.02, 0.03], [-0.05, 0.0, 0.05]], np.float32)])
+    d_ref, _ = KDTree(data=ref).query(q, 100)
+    idx = P.knn(torch.from_numpy(ref).cuda(), torch.from_numpy(q).cuda(), 100, torch.device("cuda:0")).cpu().numpy()
+    dd = np.linalg.norm(ref[idx].astype(np.float64) - q[:, None, :].astype(np.float64), axis=-1)
+    assert np.allclose(dd, d_ref, rtol=0, atol=1e-12)
+    assert all(len(set(r)) == 100 for r in idx[::50])
+
+
 def test_empty_and_single_inputs(case):
     g, sc, pmvo = case
     s, sp, f = pmvo.filter_points(torch.zeros((0, 3)))
