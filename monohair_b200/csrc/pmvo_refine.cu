@@ -9,39 +9,48 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------ refine loss
-// One warp per point, lanes over views.  With a single sample "low_conf_index" is always true
-// (sum over 1 sample < 5, PMVO.py:199) so the result is sum(l*w)/sum(w) over the views, cascade order.
-constexpr int RL_WARPS = 8;
+// RL_GROUP (64) threads per point, one view per thread; each thread scans its view's PxP patch straight from the
+// resident map with one patch row of loads in flight at a time.  With a single sample "low_conf_index" is always
+// true (sum over 1 sample < 5, PMVO.py:199) so the result is sum(l*w)/sum(w) over the views in torch.sum's cascade
+// order (done by the group's first thread from shared memory).  Launches are small (5000-point chunks of the
+// sequential refine loop), so the mapping favours latency: 64-way parallelism per point.
+constexpr int RL_GROUP = 64, RL_PTS = 4;
 
-__global__ void __launch_bounds__(RL_WARPS * 32)
+template <int PT>   // PT = patch size known at compile time (0 = generic, <= 17)
+__global__ void __launch_bounds__(RL_GROUP * RL_PTS)
 refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __restrict__ dir, int64_t N,
                    float thr_c, float* __restrict__ out_loss) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MhCam* cams = reinterpret_cast<MhCam*>(smem_raw);
-    float* lw = reinterpret_cast<float*>(cams + vw.V);          // [RL_WARPS][V][2]
-    const int V = vw.V, P = vw.P, half = P / 2, PP = P * P;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* lw = reinterpret_cast<float*>(cams + vw.V);          // [RL_PTS][V][2]
+    const int V = vw.V, P = PT ? PT : vw.P, half = P / 2;
+    const int grp = threadIdx.x / RL_GROUP, gl = threadIdx.x % RL_GROUP;
     for (int i = threadIdx.x; i < V * MH_CAM_STRIDE; i += blockDim.x) reinterpret_cast<float*>(cams)[i] = vw.cam[i];
     __syncthreads();
-    float* my = lw + (size_t)warp * V * 2;
+    float* my = lw + (size_t)grp * V * 2;
     const float Wf = (float)vw.W, Hf = (float)vw.H;
     const float2* __restrict__ mapC = reinterpret_cast<const float2*>(vw.mapC);
     const float4* __restrict__ mapP = reinterpret_cast<const float4*>(vw.mapP);
     const size_t plane = (size_t)vw.H * vw.W;
-    for (int64_t n = (int64_t)blockIdx.x * RL_WARPS + warp; n < N; n += (int64_t)gridDim.x * RL_WARPS) {
-        const float px = pts[3 * n], py = pts[3 * n + 1], pz = pts[3 * n + 2];
-        // next = p + ori * 0.005 / 4   (PMVO.py:86)
-        const float qx = px + dir[3 * n] * 0.005f / 4.0f, qy = py + dir[3 * n + 1] * 0.005f / 4.0f,
-                    qz = pz + dir[3 * n + 2] * 0.005f / 4.0f;
-        for (int v = lane; v < V; v += 32) {
+    constexpr int MAXP = PT ? PT : 17;
+    for (int64_t base_n = (int64_t)blockIdx.x * RL_PTS; base_n < N; base_n += (int64_t)gridDim.x * RL_PTS) {
+        const int64_t n = base_n + grp;
+        const bool live = n < N;
+        float px = 0, py = 0, pz = 0, qx = 0, qy = 0, qz = 0;
+        if (live) {
+            px = pts[3 * n]; py = pts[3 * n + 1]; pz = pts[3 * n + 2];
+            // next = p + ori * 0.005 / 4   (PMVO.py:86)
+            qx = px + dir[3 * n] * 0.005f / 4.0f; qy = py + dir[3 * n + 1] * 0.005f / 4.0f; qz = pz + dir[3 * n + 2] * 0.005f / 4.0f;
+        }
+        for (int v = gl; v < V && live; v += RL_GROUP) {
             const MhCam& cm = cams[v];
             float cx, cy, cz, xp, yp, xs, ys;
             mh_world_to_cam(cm.p, px, py, pz, cx, cy, cz);
             mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, cx, cy, cz, xp, yp);
             int row, col; bool oob;
             mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
-            const size_t base = (size_t)v * plane;
-            const float2 dm = __ldg(mapC + base + (size_t)row * vw.W + col);
+            const float4* __restrict__ mp = mapP + (size_t)v * plane;
+            const float2 dm = __ldg(mapC + (size_t)v * plane + (size_t)row * vw.W + col);
             float vis = mh_visible((-cz / 2.0f) * 255.0f, dm.x);
             if (oob) vis = -1.0f;
             float l_w = 0.0f, w = 0.0f;
@@ -51,19 +60,26 @@ refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __re
                 mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, c2x, c2y, c2z, xs, ys);
                 float y0, y1;
                 mh_normalize2(ys - yp, xs - xp, y0, y1);
-                const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mapP + base + (size_t)row * vw.W + col) + 3), 1e-6f), 1.0f);
+                const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mp + (size_t)row * vw.W + col) + 3), 1e-6f), 1.0f);
                 const bool hi = cmax > thr_c;
                 float bl = 0.0f, bc = 0.0f;
-                for (int p = 0; p < PP; ++p) {
-                    const int di = p / P - half, dj = p % P - half;
-                    const int r = min(max(row + di, 0), vw.H - 1), c = min(max(col + dj, 0), vw.W - 1);
-                    const float4 t = __ldg(mapP + base + (size_t)r * vw.W + c);
-                    float x0, x1;
-                    mh_normalize2(t.x, t.y, x0, x1);
-                    const float cf = fminf(fmaxf(t.z, 1e-6f), 1.0f);
-                    const float l = 1.0f - fabsf(x0 * y0 + x1 * y1);
-                    if (p == 0) { bl = l; bc = cf; }
-                    else if (l < bl && (!hi || cf > thr_c)) { bl = l; bc = cf; }
+                for (int di = 0; di < P; ++di) {
+                    const int r = min(max(row + di - half, 0), vw.H - 1);
+                    float4 t[MAXP];
+#pragma unroll
+                    for (int dj = 0; dj < MAXP; ++dj)
+                        if (dj < P) t[dj] = __ldg(mp + (size_t)r * vw.W + min(max(col + dj - half, 0), vw.W - 1));
+#pragma unroll
+                    for (int dj = 0; dj < MAXP; ++dj) {
+                        if (dj < P) {
+                            float x0, x1;
+                            mh_normalize2(t[dj].x, t[dj].y, x0, x1);
+                            const float cf = fminf(fmaxf(t[dj].z, 1e-6f), 1.0f);
+                            const float l = 1.0f - fabsf(x0 * y0 + x1 * y1);
+                            if (di == 0 && dj == 0) { bl = l; bc = cf; }
+                            else if (l < bl && (!hi || cf > thr_c)) { bl = l; bc = cf; }
+                        }
+                    }
                 }
                 w = bc;
                 l_w = bl * bc;
@@ -71,8 +87,8 @@ refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __re
             my[2 * v] = l_w;
             my[2 * v + 1] = w;
         }
-        __syncwarp();
-        if (lane == 0) {
+        __syncthreads();
+        if (gl == 0 && live) {
             MhCascade<2> acc;
             acc.init(V);
             for (int v = 0; v < V; ++v) {
@@ -81,11 +97,11 @@ refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __re
                 acc.add(0, my[2 * v]);
                 acc.add(1, my[2 * v + 1]);
             }
-            float s[2];
-            acc.finish(V, s);
-            out_loss[n] = s[0] / s[1];
+            float sres[2];
+            acc.finish(V, sres);
+            out_loss[n] = sres[0] / sres[1];
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -506,13 +522,16 @@ extern "C" int mh_pmvo_refine_loss(void* stream, const mh_views* vw, const float
     MH_CHECK_ARG(vw && vw->mapC && vw->mapP && vw->cam, "null views");
     if (N == 0) return 0;
     MH_CHECK_ARG(points && dir && loss && N > 0, "bad arguments");
-    const size_t smem = sizeof(MhCam) * vw->V + sizeof(float) * 2 * vw->V * RL_WARPS;
+    const size_t smem = sizeof(MhCam) * vw->V + sizeof(float) * 2 * vw->V * RL_PTS;
     MH_CHECK_ARG(smem <= 200 * 1024, "too many views");
-    cudaFuncSetAttribute(refine_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int64_t blocks = (N + RL_WARPS - 1) / RL_WARPS;
-    const int64_t cap = (int64_t)mh_sm_count() * 16;
+    MH_CHECK_ARG(vw->P >= 1 && vw->P <= 17 && (vw->P & 1), "patch size must be odd and <= 17");
+    auto kern = vw->P == 7 ? refine_loss_kernel<7> : vw->P == 5 ? refine_loss_kernel<5> : vw->P == 9 ? refine_loss_kernel<9>
+                                                                                                    : refine_loss_kernel<0>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = (N + RL_PTS - 1) / RL_PTS;
+    const int64_t cap = (int64_t)mh_sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    refine_loss_kernel<<<(unsigned)blocks, RL_WARPS * 32, smem, (cudaStream_t)stream>>>(*vw, points, dir, N, conf_threshold, loss);
+    kern<<<(unsigned)blocks, RL_GROUP * RL_PTS, smem, (cudaStream_t)stream>>>(*vw, points, dir, N, conf_threshold, loss);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
