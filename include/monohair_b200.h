@@ -185,9 +185,6 @@ int mh_dog_f64(void* stream, const double* image, int32_t H, int32_t W, const do
 
 /* ---- host-side test hooks (no GPU needed): the same __host__ __device__ code the kernels run ---------- */
 /* order of torch.topk(k=20, dim=0, largest, sorted) on CPU for one column of V values (PMVO.py:341). */
-/* GPU self-check: the shared-reciprocal correctly rounded division used by the kernels, against the IEEE
- * operator on n random operand triples; *mismatches_dev (device uint64, caller-zeroed) counts differing results. */
-int mh_debug_div_check(void* stream, int64_t n, uint64_t seed, uint64_t* mismatches_dev);
 int mh_debug_topk_host(const float* values_host, int32_t V, int32_t k, int32_t* idx_host, float* val_host);
 
 #ifdef __cplusplus

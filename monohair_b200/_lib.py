@@ -65,7 +65,6 @@ _SIGS = {
     "mh_filterbank_wrap_f64": (C.c_int, [p, p, i32, i32, p, i32, i32, p]),
     "mh_dog_f64": (C.c_int, [p, p, i32, i32, p, i32, p, i32, p, p]),
     "mh_debug_topk_host": (C.c_int, [p, i32, i32, p, p]),
-    "mh_debug_div_check": (C.c_int, [p, i64, C.c_uint64, p]),
 }
 
 

@@ -40,32 +40,3 @@ extern "C" int mh_debug_topk_host(const float* values, int32_t V, int32_t k, int
     for (int j = 0; j < k; ++j) { idx[j] = q[j].i; val[j] = q[j].v; }
     return 0;
 }
-
-
-// ---- GPU self-check of mh_div2 against the IEEE operator (tests/test_gpu_pmvo.py) ----
-namespace {
-__global__ void div_check_kernel(unsigned long long seed, long long n, unsigned long long* mism) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // counter-based generator (splitmix64)
-    auto mix = [](unsigned long long z) { z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-                                          z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); };
-    const unsigned long long r0 = mix(seed + 3 * i), r1 = mix(seed + 3 * i + 1), r2 = mix(seed + 3 * i + 2);
-    // mantissas uniform, exponents in the ranges the kernels see (and beyond): 2^-40 .. 2^40
-    auto mk = [](unsigned long long r) { const int e = 127 - 40 + (int)((r >> 40) % 81); const unsigned m = (unsigned)(r & 0x7fffff);
-                                         return __uint_as_float((unsigned)((r >> 63) << 31) | ((unsigned)e << 23) | m); };
-    const float a0 = mk(r0), a1 = (i & 7) == 0 ? 0.0f : mk(r1), b = mk(r2);
-    float q0, q1;
-    mh_div2(a0, a1, b, q0, q1);
-    const float e0 = __fdiv_rn(a0, b), e1 = __fdiv_rn(a1, b);
-    if (__float_as_uint(q0) != __float_as_uint(e0) || __float_as_uint(q1) != __float_as_uint(e1)) atomicAdd(mism, 1ull);
-}
-}  // namespace
-
-extern "C" int mh_debug_div_check(void* stream, int64_t n, uint64_t seed, uint64_t* mismatches_dev) {
-    MH_CHECK_ARG(mismatches_dev && n > 0, "bad arguments");
-    div_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, n, (unsigned long long*)mismatches_dev);
-    MH_COUNT_LAUNCH();
-    MH_CHECK_LAUNCH();
-    return 0;
-}

@@ -200,15 +200,6 @@ def test_knn_exact_vs_kdtree():
     assert np.mean(idx == i_ref) > 0.9999
 
 
-def test_shared_reciprocal_division_is_ieee_exact():
-    from monohair_b200 import _lib
-    L = _lib.lib()
-    mism = torch.zeros(1, dtype=torch.int64, device="cuda:0")
-    for seed in (1, 2, 3, 4):
-        _lib.check(L.mh_debug_div_check(_lib.stream_ptr("cuda:0"), 1 << 26, seed, _lib.ptr(mism)), "mh_debug_div_check")
-    assert int(mism.item()) == 0, f"{int(mism.item())} of 2^28 quotients differ from the IEEE operator"
-
-
 def test_knn_fallback_paths():
     """dense clumps (buffer overflow) and hundreds of coincident points (no separating radius) take the general
     kernel; results must still be the exact k nearest by distance."""
