@@ -55,6 +55,12 @@ int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,
                   const float* conf /*[H][W]*/, const float* mask, int32_t mask_stride,
                   void* mapC /*[V][H][W] float2*/, void* mapP /*[V][H][W] float4*/);
 
+/* Same for the dtypes the reference's loaders produce (depth float32; Ori, Conf, mask float64): the float cast of
+ * PMVO.py:23-26 is fused into the pack. */
+int mh_views_pack_f64(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,
+                      const float* depth, int32_t depth_stride, const double* ori /*[H][W][2]*/,
+                      const double* conf /*[H][W]*/, const double* mask, int32_t mask_stride, void* mapC, void* mapP);
+
 /* Same from the on-disk 8-bit formats (best_ori gray, conf, mask) with the decode of
  * Load_Ori_And_Conf / load_mask (PMVO_utils.py:255-313) fused; lut = 256x2 floats {sin o, cos o} built on host. */
 int mh_views_pack_u8(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,

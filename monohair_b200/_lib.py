@@ -36,6 +36,7 @@ _SIGS = {
     "mh_launch_count": (i64, []),
     "mh_views_pack_camera_host": (C.c_int, [p, p, p, p]),
     "mh_views_pack": (C.c_int, [p, i32, i32, i32, i32, p, i32, p, p, p, i32, p, p]),
+    "mh_views_pack_f64": (C.c_int, [p, i32, i32, i32, i32, p, i32, p, p, p, i32, p, p]),
     "mh_views_pack_u8": (C.c_int, [p, i32, i32, i32, i32, p, i32, p, p, p, p, p, p, p, p]),
     "mh_filter_count": (C.c_int, [p, VP, p, i64, f32, f32, p]),
     "mh_filter_decide": (C.c_int, [p, p, i64, p, p]),

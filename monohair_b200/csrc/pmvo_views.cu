@@ -64,6 +64,33 @@ extern "C" int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int3
     return 0;
 }
 
+// Same as mh_views_pack for the dtypes the reference's loaders actually hand to PMVO.__init__ (PMVO_utils.py:255-313):
+// depth float32, Ori / Conf / mask float64.  The float64 -> float32 rounding of PMVO.py:23-26 (.type(torch.float))
+// happens here, so the host side only issues the raw H2D copies.
+extern "C" int mh_views_pack_f64(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,
+                                 const float* depth, int32_t depth_stride, const double* ori, const double* conf,
+                                 const double* mask, int32_t mask_stride, void* mapC_, void* mapP_) {
+    MH_CHECK_ARG(depth && ori && conf && mask && mapC_ && mapP_, "null pointer");
+    MH_CHECK_ARG(H > 0 && W > 0 && v >= 0, "bad size");
+    MH_CHECK_ARG(P >= 1 && (P & 1) && P / 2 <= MAX_HALF, "patch size must be odd and <= 17");
+    float2* mapC = reinterpret_cast<float2*>(mapC_) + (size_t)v * H * W;
+    float4* mapP = reinterpret_cast<float4*>(mapP_) + (size_t)v * H * W;
+    dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
+    auto conf_at = [=] __device__(int y, int x) { return (float)__ldg(conf + (size_t)y * W + x); };
+    auto emit = [=] __device__(int y, int x, float cmax) {
+        size_t i = (size_t)y * W + x;
+        float m = (float)__ldg(mask + i * mask_stride);
+        m = (m > 0.2f) ? 1.0f : m;
+        mapC[i] = make_float2(__ldg(depth + i * depth_stride), m);
+        const double2 o = __ldg(reinterpret_cast<const double2*>(ori) + i);
+        mapP[i] = make_float4((float)o.x, (float)o.y, (float)__ldg(conf + i), cmax);
+    };
+    pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
+    MH_COUNT_LAUNCH();
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int mh_views_pack_u8(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,
                                 const float* depth, int32_t depth_stride, const uint8_t* ori_gray,
                                 const uint8_t* conf_u8, const uint8_t* mask_u8, const float* ori_lut,

@@ -63,18 +63,35 @@ class PMVO(nn.Module):
             self.mapP = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
             self.cam = torch.stack([c.record() for c in self.camera]).to(dev).contiguous()
             st = stream_ptr(dev)
+            stage = {}
+
+            def to_dev(a):
+                """raw H2D copy into a reusable staging buffer (async when the source is pinned): the copy of
+                PMVO.py:23-26; the float cast is fused into the pack kernel."""
+                t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+                key = (t.dtype, tuple(t.shape))
+                if key not in stage:
+                    stage[key] = [torch.empty(t.shape, dtype=t.dtype, device=dev) for _ in range(2)]
+                buf = stage[key][0]
+                stage[key].reverse()
+                buf.copy_(t, non_blocking=True)
+                return buf
+
             for v, k in enumerate(self.camera_key):
-                # the H2D copy + float cast of PMVO.py:23-26, then the pack kernel
-                d = _f32(depths[k], dev)
-                o = _f32(Ori[k], dev)
-                c = _f32(Conf[k], dev)
-                m = _f32(masks[k], dev)
+                d_h, o_h, c_h, m_h = depths[k], Ori[k], Conf[k], masks[k]
+                dts = [(x.dtype if torch.is_tensor(x) else torch.from_numpy(np.asarray(x)[:0].copy()).dtype) for x in (d_h, o_h, c_h, m_h)]
+                f64_path = dts[0] == torch.float32 and all(t == torch.float64 for t in dts[1:])
+                if f64_path:
+                    d, o, c, m = to_dev(d_h), to_dev(o_h), to_dev(c_h), to_dev(m_h)
+                else:
+                    d, o, c, m = _f32(d_h, dev), _f32(o_h, dev), _f32(c_h, dev), _f32(m_h, dev)
                 assert d.shape[:2] == (H, W) and o.shape == (H, W, 2) and c.shape == (H, W) and m.shape[:2] == (H, W), \
                     f"view {k}: map shapes do not match image_size {image_size}"
                 ds = d.shape[2] if d.dim() == 3 else 1
                 ms = m.shape[2] if m.dim() == 3 else 1
-                check(lib().mh_views_pack(st, v, H, W, self.patch_size, ptr(d), ds, ptr(o), ptr(c), ptr(m), ms,
-                                          ptr(self.mapC), ptr(self.mapP)), "mh_views_pack")
+                fn = lib().mh_views_pack_f64 if f64_path else lib().mh_views_pack
+                check(fn(st, v, H, W, self.patch_size, ptr(d), ds, ptr(o), ptr(c), ptr(m), ms,
+                         ptr(self.mapC), ptr(self.mapP)), "mh_views_pack")
         self._views = MhViews(V, H, W, self.patch_size, self.mapC.data_ptr(), self.mapP.data_ptr(), self.cam.data_ptr())
         self._offsets = self._sample_offsets(90).to(dev)
 
@@ -154,7 +171,7 @@ class PMVO(nn.Module):
         ori = torch.empty((N, 3), dtype=torch.float32, device=dev)
         loss = torch.empty((N,), dtype=torch.float32, device=dev)
         hc = torch.empty((N,), dtype=torch.uint8, device=dev)
-        ws = torch.empty((256,), dtype=torch.uint8, device=dev)
+        ws = torch.empty((int(lib().mh_pmvo_optimize_workspace_bytes(self._vp(), N)),), dtype=torch.uint8, device=dev)
         dbg = {}
         if debug:
             dbg = {"base_idx": torch.empty((_lib.MH_TOPK, N), dtype=torch.int32, device=dev),
