@@ -207,7 +207,7 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
                 float thr_c, float* __restrict__ out_ori, float* __restrict__ out_loss,
                 uint8_t* __restrict__ out_hc, int32_t* __restrict__ dbg_bidx, float* __restrict__ dbg_bval,
                 float* __restrict__ dbg_best, float* __restrict__ dbg_loss_b, int32_t* __restrict__ dbg_arg_b,
-                unsigned long long* __restrict__ work_counter, const MhKV* __restrict__ topk_in) {
+                unsigned long long* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem sm;
     const int V = vw.V, P = vw.P, PP = P * P, half = P / 2;
@@ -245,15 +245,16 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
             const float confp = (vis < 1.0f) ? conf * fmaxf(vis, 0.0f) : conf;      // :340
             sm.camz[v] = cz; sm.xp[v] = xp; sm.yp[v] = yp; sm.vis[v] = vis;
             sm.orr[v] = oc.x; sm.orc[v] = oc.y; sm.pix[v] = pix;
-            (void)confp;
+            sm.q[v].v = confp; sm.q[v].i = v;
         }
-        // ---- B: base views come from the pre-pass (topk_kernel): torch.topk order over Conf' ----
-        if (tid < MH_TOPK) sm.q[tid] = topk_in[(size_t)n * MH_TOPK + tid];
         __syncthreads();
 
-        {
+        if (warp == 0) {
+            // ---- B: base views ----
+            if (lane == 0) mh_topk_torch_cpu(sm.q, V, MH_TOPK);
+        } else {
             // ---- A2: stage patches of visible views ----
-            if (warp == 0) {
+            if (warp == 1) {
                 int cnt = 0;
                 for (int v0 = 0; v0 < V; v0 += 32) {
                     const int v = v0 + lane;
@@ -264,7 +265,7 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
                 }
                 if (lane == 0) sm.misc[0] = cnt;
             }
-            for (int v = warp; v < V; v += OPT_WARPS) {
+            for (int v = warp - 1; v < V; v += OPT_WARPS - 1) {
                 if (sm.vis[v] == -1.0f) { if (lane == 0) sm.ecnt[v] = 0; continue; }
                 const int pix = sm.pix[v];
                 const int row = pix / vw.W, col = pix - row * vw.W;
@@ -288,13 +289,12 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
                         // duplicate of an entry already kept in an earlier 32-chunk?
                         if (elig) for (int k = 0; k < kept; ++k) if (sxy[k].x == ex0 && sxy[k].y == ex1) { elig = false; break; }
                     }
-                    // duplicate of an earlier eligible lane in this chunk?
-                    bool dup = false;
-                    for (int l2 = 0; l2 < 31; ++l2) {
-                        const float ox0 = __shfl_sync(0xffffffffu, ex0, l2), ox1 = __shfl_sync(0xffffffffu, ex1, l2);
-                        const bool oel = __shfl_sync(0xffffffffu, (int)elig, l2) != 0;
-                        if (l2 < lane && oel && ox0 == ex0 && ox1 == ex1) dup = true;
-                    }
+                    // duplicate of an earlier eligible lane in this chunk?  (bitwise match: -0/+0 are kept apart,
+                    // which only keeps a harmless extra entry)
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(ex0) << 32) | __float_as_uint(ex1);
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    const unsigned em = __ballot_sync(0xffffffffu, elig);
+                    const bool dup = (peers & em & ((1u << lane) - 1)) != 0;
                     const bool keep = elig && !dup;
                     const unsigned m = __ballot_sync(0xffffffffu, keep);
                     __syncwarp();
@@ -345,45 +345,8 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
     }
 }
 
-// Pre-pass, one thread per point: Conf' over all views (Compute_Visible_and_Ori centre values + :340) and the
-// torch.topk(20) order.  Thousands of independent points per SM hide the latency of this inherently serial
-// (introselect / introsort emulation) code, which used to sit on the critical path of every CTA.
-constexpr int TOPK_MAXV = 128;
-
-__global__ void __launch_bounds__(128)
-topk_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, MhKV* __restrict__ out) {
-    __shared__ MhCam cams[TOPK_MAXV];
-    for (int i = threadIdx.x; i < vw.V * MH_CAM_STRIDE; i += blockDim.x) reinterpret_cast<float*>(cams)[i] = vw.cam[i];
-    __syncthreads();
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const float px = pts[3 * n], py = pts[3 * n + 1], pz = pts[3 * n + 2];
-    const float Wf = (float)vw.W, Hf = (float)vw.H;
-    const float2* __restrict__ mapC = reinterpret_cast<const float2*>(vw.mapC);
-    const float4* __restrict__ mapP = reinterpret_cast<const float4*>(vw.mapP);
-    const size_t plane = (size_t)vw.H * vw.W;
-    MhKV q[TOPK_MAXV];
-    for (int v = 0; v < vw.V; ++v) {
-        const MhCam& cm = cams[v];
-        float cx, cy, cz, xp, yp;
-        mh_world_to_cam(cm.p, px, py, pz, cx, cy, cz);
-        mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, cx, cy, cz, xp, yp);
-        int row, col; bool oob;
-        mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
-        const size_t pix = (size_t)v * plane + (size_t)row * vw.W + col;
-        const float2 dm = __ldg(mapC + pix);
-        float vis = mh_visible((-cz / 2.0f) * 255.0f, dm.x);
-        if (oob) vis = -1.0f;
-        const float conf = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mapP + pix) + 2), 1e-6f), 1.0f);
-        q[v].v = (vis < 1.0f) ? conf * fmaxf(vis, 0.0f) : conf;                  // :340
-        q[v].i = v;
-    }
-    mh_topk_torch_cpu(q, vw.V, MH_TOPK);
-    for (int k = 0; k < MH_TOPK; ++k) out[(size_t)n * MH_TOPK + k] = q[k];
-}
-
 typedef void (*OptKernel)(mh_views, const float*, int64_t, const float*, int, float, float*, float*, uint8_t*, int32_t*,
-                          float*, float*, float*, int32_t*, unsigned long long*, const MhKV*);
+                          float*, float*, float*, int32_t*, unsigned long long*);
 
 OptKernel pick_kernel(int S, int V) {
     const int spl = (S + 31) / 32;
@@ -399,8 +362,8 @@ OptKernel pick_kernel(int S, int V) {
 }  // namespace
 
 extern "C" int64_t mh_pmvo_optimize_workspace_bytes(const mh_views* views, int64_t N) {
-    (void)views;
-    return 256 + (int64_t)sizeof(MhKV) * MH_TOPK * (N > 0 ? N : 0);          // work counter + per-point top-k
+    (void)views; (void)N;
+    return 256;          // the work counter
 }
 
 extern "C" int mh_pmvo_optimize(void* stream, const mh_views* vw, const float* points, int64_t N,
@@ -411,8 +374,7 @@ extern "C" int mh_pmvo_optimize(void* stream, const mh_views* vw, const float* p
     MH_CHECK_ARG(vw && vw->mapC && vw->mapP && vw->cam, "null views");
     if (N == 0) return 0;
     MH_CHECK_ARG(points && offsets && ori && loss && high_conf && workspace && N > 0, "null pointer");
-    MH_CHECK_ARG(workspace_bytes >= mh_pmvo_optimize_workspace_bytes(vw, N), "workspace too small");
-    MH_CHECK_ARG(vw->V <= TOPK_MAXV, "more than 128 views are not supported by the top-k pre-pass");
+    MH_CHECK_ARG(workspace_bytes >= 256, "workspace too small");
     MH_CHECK_ARG(vw->V >= MH_TOPK, "PMVO.forward needs at least 20 views (torch.topk(...,20), PMVO.py:341)");
     MH_CHECK_ARG(S >= 1 && S <= 32 * MAX_SPL, "num_sample must be in [1,128]");
     MH_CHECK_ARG((vw->P & 1) && vw->P >= 1, "patch size must be odd");
@@ -436,12 +398,9 @@ extern "C" int mh_pmvo_optimize(void* stream, const mh_views* vw, const float* p
     int64_t grid = (int64_t)mh_sm_count() * per_sm;
     if (grid > N) grid = N;
     cudaMemsetAsync(workspace, 0, 8, (cudaStream_t)stream);
-    MhKV* topk = reinterpret_cast<MhKV*>(reinterpret_cast<char*>(workspace) + 256);
-    topk_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*vw, points, N, topk);
-    MH_COUNT_LAUNCH();
     kern<<<(unsigned)grid, OPT_THREADS, smem, (cudaStream_t)stream>>>(
         *vw, points, N, offsets, S, conf_threshold, ori, loss, high_conf, dbg_base_idx, dbg_base_val,
-        dbg_best_sample, dbg_loss_b, dbg_arg_b, reinterpret_cast<unsigned long long*>(workspace), topk);
+        dbg_best_sample, dbg_loss_b, dbg_arg_b, reinterpret_cast<unsigned long long*>(workspace));
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
