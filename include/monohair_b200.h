@@ -133,6 +133,12 @@ int mh_medoid_gather(void* stream, const float* ori /*[n_ref][3]*/, const int32_
 int mh_refine_update(void* stream, const float* center, const float* upd_loss, const uint8_t* head_filter,
                      int64_t n, float* ori /*in/out [n][3]*/, float* loss /*out [n]*/);
 
+/* The whole chunk-sequential pass of PMVO.refine step (i) (PMVO.py:608-641): for each chunk of sub_num points, in
+ * order: mh_medoid_gather on the CURRENT ori -> mh_pmvo_refine_loss -> mh_refine_update in place. */
+int mh_refine_chunks(void* stream, const mh_views* views, const float* points, const int32_t* nbr, int32_t K,
+                     const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
+                     float* ori /*in/out*/, float* loss /*out*/, float* scratch /*[sub_num][4] floats*/);
+
 /* ---- voxel fusion (PMVO.py:695-726, PMVO_utils.p2v :386-404) ------------------------------------------ */
 int64_t mh_voxel_fuse_workspace_bytes(int64_t n_points, int32_t gx, int32_t gy, int32_t gz);
 /* points float32 [n][3] (world), dirs float32 [n][3].  Flips dirs to dir.y<=0 (PMVO.py:702-703), voxelises with
@@ -142,6 +148,9 @@ int64_t mh_voxel_fuse_workspace_bytes(int64_t n_points, int32_t gx, int32_t gy, 
 int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
                   const double* voxel_min_host /*[3]*/, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
                   void* volume /*float4 [gz][gy][gx]*/, int32_t* vox_index, void* workspace, int64_t workspace_bytes);
+/* Synchronous: largest per-voxel point count seen by the last mh_voxel_fuse on this workspace (voxels holding
+ * more than 1024 points are fused from 1024 of them; the host raises if that ever happens). */
+int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host);
 /* Overwrite voxels with given orientations, last writer wins (raw.npy merge, PMVO.py:747-749). */
 int mh_voxel_overwrite(void* stream, const float* points, const float* dirs, int64_t n,
                        const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,

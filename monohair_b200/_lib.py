@@ -44,6 +44,7 @@ _SIGS = {
     "mh_head_count": (C.c_int, [p, VP, p, i64, f32, p]),
     "mh_head_decide": (C.c_int, [p, p, p, p, i64, f64, f64, p]),
     "mh_centre_gather": (C.c_int, [p, VP, p, i64, p, p, p, p, p]),
+    "mh_refine_chunks": (C.c_int, [p, VP, p, p, i32, p, i64, i64, f32, p, p, p]),
     "mh_refine_update": (C.c_int, [p, p, p, p, i64, p, p]),
     "mh_pmvo_optimize_workspace_bytes": (i64, [VP, i64]),
     "mh_pmvo_optimize": (C.c_int, [p, VP, p, i64, p, i32, f32, p, p, p, p, p, p, p, p, p, i64]),
@@ -54,6 +55,7 @@ _SIGS = {
     "mh_medoid_gather": (C.c_int, [p, p, p, i64, i32, p, p]),
     "mh_voxel_fuse_workspace_bytes": (i64, [i64, i32, i32, i32]),
     "mh_voxel_fuse": (C.c_int, [p, p, p, i64, p, f64, i32, i32, i32, p, p, p, i64]),
+    "mh_voxel_fuse_max_points": (C.c_int, [p, p]),
     "mh_voxel_overwrite": (C.c_int, [p, p, p, i64, p, f64, i32, i32, i32, p, p]),
     "mh_volume_to_mat": (C.c_int, [p, p, i32, i32, i32, p, p]),
     "mh_volume_from_mat": (C.c_int, [p, p, p, i32, i32, i32, p]),

@@ -14,7 +14,6 @@
 #include "mh_common.cuh"
 #include "mh_torch_sum.cuh"
 
-int mh_exclusive_scan(cudaStream_t st, const int* in, int* out, int64_t n, int* scratch);   // pmvo_refine.cu
 
 namespace {
 
@@ -31,8 +30,17 @@ __device__ __forceinline__ void p2v(const VGrid& g, float px, float py, float pz
     z = (int)fmin(fmax(fz, 0.0), (double)(g.gz - 1));
 }
 
-__global__ void key_kernel(VGrid g, const float* __restrict__ pts, int64_t n, int* __restrict__ key,
-                           int* __restrict__ counts, int* __restrict__ vox_index) {
+// flipped direction of point i (PMVO.py:702-703: ori[ori.y>0] *= -1)
+__device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, float& a, float& b, float& c) {
+    a = dirs[3 * i]; b = dirs[3 * i + 1]; c = dirs[3 * i + 2];
+    if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
+}
+
+// Pass 1: voxel key of every point and a per-voxel linked list threaded through next[]; the list head lives in the
+// (zeroed) volume itself, in the .w slot of the voxel's float4, as the integer id+1 of the last point inserted.
+__global__ void __launch_bounds__(256)
+link_kernel(VGrid g, const float* __restrict__ pts, int64_t n, float4* __restrict__ volume, int* __restrict__ next,
+            int* __restrict__ key, int* __restrict__ vox_index) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int x, y, z;
@@ -40,127 +48,110 @@ __global__ void key_kernel(VGrid g, const float* __restrict__ pts, int64_t n, in
     const int k = (z * g.gy + y) * g.gx + x;
     key[i] = k;
     if (vox_index) vox_index[i] = (x * g.gy + y) * g.gz + z;
-    atomicAdd(counts + k, 1);
+    next[i] = atomicExch(reinterpret_cast<int*>(volume + k) + 3, (int)i + 1);
 }
 
-__global__ void fill_kernel(const int* __restrict__ key, int64_t n, const int* __restrict__ starts,
-                            int* __restrict__ cursor, int* __restrict__ items) {
+// Pass 2: the point that is its voxel's list head resolves the voxel.  Up to 4 points are handled in registers
+// (ids sorted back into original order, medoid under |cos| -- for K <= 4 torch.mean's order is the plain sequential
+// sum); larger voxels go to a work list for the warp-per-voxel kernel.
+__global__ void __launch_bounds__(256)
+head_kernel(int64_t n, const int* __restrict__ key, const int* __restrict__ next, const float* __restrict__ dirs,
+            float4* __restrict__ volume, int* __restrict__ worklist, int* __restrict__ wl_count, int* __restrict__ max_k) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int k = key[i];
-    items[starts[k] + atomicAdd(cursor + k, 1)] = (int)i;
-}
-
-// flipped direction of point i (PMVO.py:702-703: ori[ori.y>0] *= -1), normalised like cosine_similarity does
-__device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, float& a, float& b, float& c) {
-    a = dirs[3 * i]; b = dirs[3 * i + 1]; c = dirs[3 * i + 2];
-    if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
-}
-
-// Pass 4a: streaming.  Empty voxels -> zeros, single-point voxels -> that point's (flipped) direction,
-// multi-point voxels -> appended to a work list for pass 4b.  Reads 8 B, writes 16 B per voxel, fully coalesced.
-__global__ void __launch_bounds__(256)
-fuse_stream_kernel(int64_t nvox, const int* __restrict__ starts, const int* __restrict__ items,
-                   const float* __restrict__ dirs, float4* __restrict__ volume, int* __restrict__ worklist,
-                   int* __restrict__ wl_count) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool multi = false;
-    if (g < nvox) {
-        const int s = starts[g], e = starts[g + 1];
-        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e - s == 1) {
-            float o0, o1, o2;
-            load_dir(dirs, items[s], o0, o1, o2);
-            out = make_float4(o0, -o1, -o2, 1.0f);
+    if (__float_as_int(volume[k].w) != (int)i + 1) return;
+    int id[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (int j = (int)i + 1; j != 0; j = next[j - 1]) { if (cnt < 4) id[cnt] = j - 1; ++cnt; }
+    if (cnt > 4) {
+        worklist[atomicAdd(wl_count, 1)] = k;
+        atomicMax(max_k, cnt);
+        return;
+    }
+    // sort ids ascending (original point order decides argmax ties)
+    for (int a = 1; a < cnt; ++a) for (int b = a; b > 0 && id[b - 1] > id[b]; --b) { const int t_ = id[b]; id[b] = id[b - 1]; id[b - 1] = t_; }
+    float u[4][3], raw[4][3];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        if (a < cnt) {
+            load_dir(dirs, id[a], raw[a][0], raw[a][1], raw[a][2]);
+            const float nn = fmaxf(mh_norm3(raw[a][0], raw[a][1], raw[a][2]), 1e-8f);
+            u[a][0] = raw[a][0] / nn; u[a][1] = raw[a][1] / nn; u[a][2] = raw[a][2] / nn;
+        } else { u[a][0] = u[a][1] = u[a][2] = raw[a][0] = raw[a][1] = raw[a][2] = 0.0f; }
+    }
+    int bk = 0;
+    if (cnt > 1) {
+        float best = -1e30f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (a < cnt) {
+                float sum = 0.0f;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b < cnt) sum += fabsf((u[a][0] * u[b][0] + u[a][1] * u[b][1]) + u[a][2] * u[b][2]);
+                sum = sum / (float)cnt;
+                if (sum > best) { best = sum; bk = a; }
+            }
         }
-        multi = e - s > 1;
-        volume[g] = out;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, multi);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(wl_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (multi) worklist[base + __popc(m & ((1u << lane) - 1))] = (int)g;
-    }
+    float o0 = raw[0][0], o1 = raw[0][1], o2 = raw[0][2];
+#pragma unroll
+    for (int a = 1; a < 4; ++a) if (bk == a) { o0 = raw[a][0]; o1 = raw[a][1]; o2 = raw[a][2]; }
+    volume[k] = make_float4(o0, -o1, -o2, 1.0f);
 }
 
-// Pass 4b: one warp per multi-point voxel.  Restores the original point order inside the bucket (the atomics of
-// pass 3 filled it in arbitrary order; argmax ties go to the first point) and takes the medoid under |cos| with
-// torch.mean's summation order (compute_points_similarity, PMVO_utils.py:366-382).
-constexpr int FUSE_WARPS = 4, FUSE_MAXK = 128;
+// Pass 3: one warp per voxel with more than 4 points: ids gathered from the list, rank-sorted into original order,
+// medoid under |cos| with torch.mean's summation order (compute_points_similarity, PMVO_utils.py:366-382).
+constexpr int FUSE_WARPS = 4, FUSE_MAXK = 1024;
 
 __global__ void __launch_bounds__(FUSE_WARPS * 32)
-fuse_medoid_kernel(const int* __restrict__ worklist, const int* __restrict__ wl_count, const int* __restrict__ starts,
-                   int* __restrict__ items, const float* __restrict__ dirs, float4* __restrict__ volume) {
-    __shared__ int s_idx[FUSE_WARPS][FUSE_MAXK];
-    __shared__ float s_u[FUSE_WARPS][FUSE_MAXK * 3];
+fuse_medoid_kernel(const int* __restrict__ worklist, const int* __restrict__ wl_count, const int* __restrict__ next,
+                   const float* __restrict__ dirs, float4* __restrict__ volume) {
+    extern __shared__ __align__(16) unsigned char fm_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = *wl_count;
-    for (int w = blockIdx.x * FUSE_WARPS + warp; w < n; w += gridDim.x * FUSE_WARPS) {
+    int* s_raw = reinterpret_cast<int*>(fm_smem) + (size_t)warp * FUSE_MAXK * 5;      // [MAXK] unsorted ids
+    int* s_idx = s_raw + FUSE_MAXK;                                                  // [MAXK] sorted ids
+    float* u = reinterpret_cast<float*>(s_idx + FUSE_MAXK);                           // [MAXK][3]
+    const int nwl = *wl_count;
+    for (int w = blockIdx.x * FUSE_WARPS + warp; w < nwl; w += gridDim.x * FUSE_WARPS) {
         const int g = worklist[w];
-        const int s = starts[g], K = starts[g + 1] - s;
-        int bk = 0;
-        if (K <= FUSE_MAXK) {
-            // rank sort by point id
-            for (int a = lane; a < K; a += 32) {
-                const int v = items[s + a];
-                int rank = 0;
-                for (int b = 0; b < K; ++b) rank += (items[s + b] < v) ? 1 : 0;
-                s_idx[warp][rank] = v;
-            }
-            __syncwarp();
-            for (int a = lane; a < K; a += 32) {
-                float a0, a1, a2;
-                load_dir(dirs, s_idx[warp][a], a0, a1, a2);
-                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
-                s_u[warp][3 * a] = a0 / na; s_u[warp][3 * a + 1] = a1 / na; s_u[warp][3 * a + 2] = a2 / na;
-            }
-            __syncwarp();
-            float best = -1e30f; bk = 0x7fffffff;
-            const float* u = s_u[warp];
-            for (int k = lane; k < K; k += 32) {
-                const float a0 = u[3 * k], a1 = u[3 * k + 1], a2 = u[3 * k + 2];
-                float sum = mh_torch_inner_sum(K, [&](int j) { return fabsf((a0 * u[3 * j] + a1 * u[3 * j + 1]) + a2 * u[3 * j + 2]); });
-                sum = sum / (float)K;
-                if (sum > best) { best = sum; bk = k; }
-            }
+        int K = 0;
+        if (lane == 0) {
+            for (int j = __float_as_int(volume[g].w); j != 0 && K < FUSE_MAXK; j = next[j - 1]) s_raw[K++] = j - 1;
+        }
+        K = __shfl_sync(0xffffffffu, K, 0);
+        __syncwarp();
+        for (int a = lane; a < K; a += 32) {
+            const int v = s_raw[a];
+            int rank = 0;
+            for (int b = 0; b < K; ++b) rank += (s_raw[b] < v) ? 1 : 0;
+            s_idx[rank] = v;
+        }
+        __syncwarp();
+        for (int a = lane; a < K; a += 32) {
+            float a0, a1, a2;
+            load_dir(dirs, s_idx[a], a0, a1, a2);
+            const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
+            u[3 * a] = a0 / na; u[3 * a + 1] = a1 / na; u[3 * a + 2] = a2 / na;
+        }
+        __syncwarp();
+        float best = -1e30f; int bk = 0x7fffffff;
+        for (int k = lane; k < K; k += 32) {
+            const float a0 = u[3 * k], a1 = u[3 * k + 1], a2 = u[3 * k + 2];
+            float sum = mh_torch_inner_sum(K, [&](int j) { return fabsf((a0 * u[3 * j] + a1 * u[3 * j + 1]) + a2 * u[3 * j + 2]); });
+            sum = sum / (float)K;
+            if (sum > best) { best = sum; bk = k; }
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
-            }
-            if (lane == 0) {
-                float o0, o1, o2;
-                load_dir(dirs, s_idx[warp][bk], o0, o1, o2);
-                volume[g] = make_float4(o0, -o1, -o2, 1.0f);
-            }
-        } else if (lane == 0) {
-            // rare: very crowded voxel, serial path in global memory
-            for (int a = s + 1; a < s + K; ++a) {
-                const int v = items[a];
-                int b = a - 1;
-                while (b >= s && items[b] > v) { items[b + 1] = items[b]; --b; }
-                items[b + 1] = v;
-            }
-            float best = -1e30f;
-            for (int k = 0; k < K; ++k) {
-                float a0, a1, a2;
-                load_dir(dirs, items[s + k], a0, a1, a2);
-                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
-                a0 = a0 / na; a1 = a1 / na; a2 = a2 / na;
-                float sum = mh_torch_inner_sum(K, [&](int j) {
-                    float b0, b1, b2;
-                    load_dir(dirs, items[s + j], b0, b1, b2);
-                    const float nb = fmaxf(mh_norm3(b0, b1, b2), 1e-8f);
-                    return fabsf((a0 * (b0 / nb) + a1 * (b1 / nb)) + a2 * (b2 / nb)); });
-                sum = sum / (float)K;
-                if (sum > best) { best = sum; bk = k; }
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+        }
+        if (lane == 0) {
             float o0, o1, o2;
-            load_dir(dirs, items[s + bk], o0, o1, o2);
+            load_dir(dirs, s_idx[bk], o0, o1, o2);
             volume[g] = make_float4(o0, -o1, -o2, 1.0f);
         }
         __syncwarp();
@@ -237,10 +228,10 @@ VGrid make_grid(const double* vmin, double vs, int gx, int gy, int gz) {
 
 }  // namespace
 
-// workspace: [counts nvox+4][starts nvox+4][cursor nvox+4][key n][items n][worklist n/2+4][wl_count 4][scan scratch]
+// workspace: [hdr 64 B: wl_count, max_k][next n][key n][worklist n/5+4]
 extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
-    const int64_t nvox = (int64_t)gx * gy * gz;
-    return 4 * (3 * (nvox + 4) + 2 * n + (n / 2 + 4) + 4 + nvox / 4096 + 64);
+    (void)gx; (void)gy; (void)gz;
+    return 64 + 4 * (2 * n + n / 5 + 8);
 }
 
 extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
@@ -248,35 +239,40 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
                              void* volume, int32_t* vox_index, void* workspace, int64_t workspace_bytes) {
     MH_CHECK_ARG(volume && workspace && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
     MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && voxel_size > 0, "bad grid");
-    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31), "grid or point count too large for int32 keys");
+    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31) - 1, "grid or point count too large for int32 keys");
     MH_CHECK_ARG(workspace_bytes >= mh_voxel_fuse_workspace_bytes(n, gx, gy, gz), "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nvox = (int64_t)gx * gy * gz;
     const VGrid g = make_grid(voxel_min_host, voxel_size, gx, gy, gz);
-    int* counts = reinterpret_cast<int*>(workspace);
-    int* starts = counts + (nvox + 4);
-    int* cursor = starts + (nvox + 4);
-    int* key = cursor + (nvox + 4);
-    int* items = key + n;
-    int* worklist = items + n;
-    int* wl_count = worklist + (n / 2 + 4);
-    int* scratch = wl_count + 4;
-    cudaMemsetAsync(wl_count, 0, sizeof(int), st);
-    cudaMemsetAsync(counts, 0, sizeof(int) * (nvox + 1), st);
-    cudaMemsetAsync(cursor, 0, sizeof(int) * nvox, st);
-    if (n > 0) { key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, n, key, counts, vox_index); MH_COUNT_LAUNCH(); }
-    mh_exclusive_scan(st, counts, starts, nvox, scratch);
-    if (n > 0) { fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, starts, cursor, items); MH_COUNT_LAUNCH(); }
-    fuse_stream_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, st>>>(nvox, starts, items, dirs, reinterpret_cast<float4*>(volume), worklist, wl_count);
+    int* hdr = reinterpret_cast<int*>(workspace);
+    int* next = hdr + 16;
+    int* key = next + n;
+    int* worklist = key + n;
+    cudaMemsetAsync(hdr, 0, 64, st);
+    cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, st);            // empty voxels: the streaming 16 B/voxel write
+    if (n == 0) return 0;
+    link_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, n, reinterpret_cast<float4*>(volume), next, key, vox_index);
     MH_COUNT_LAUNCH();
-    if (n > 1) {
-        int64_t blocks = (n / 2 + FUSE_WARPS - 1) / FUSE_WARPS;
-        const int64_t cap = (int64_t)mh_sm_count() * 16;
-        if (blocks > cap) blocks = cap;
-        fuse_medoid_kernel<<<(unsigned)blocks, FUSE_WARPS * 32, 0, st>>>(worklist, wl_count, starts, items, dirs, reinterpret_cast<float4*>(volume));
-        MH_COUNT_LAUNCH();
-    }
+    head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, key, next, dirs, reinterpret_cast<float4*>(volume), worklist, hdr, hdr + 1);
+    MH_COUNT_LAUNCH();
+    const size_t smem = (size_t)FUSE_WARPS * FUSE_MAXK * 5 * sizeof(int);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(fuse_medoid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    int64_t blocks = (n / 5 + FUSE_WARPS) / FUSE_WARPS;
+    const int64_t cap = (int64_t)mh_sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    fuse_medoid_kernel<<<(unsigned)blocks, FUSE_WARPS * 32, smem, st>>>(worklist, hdr, next, dirs, reinterpret_cast<float4*>(volume));
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
+    return 0;
+}
+
+/* after synchronising the stream: the largest number of points that fell into one voxel in the last mh_voxel_fuse
+ * call on this workspace; voxels with more than 1024 points are fused from their first 1024 (in list order). */
+extern "C" int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host) {
+    MH_CHECK_ARG(workspace && max_k_host, "null pointer");
+    cudaError_t e = cudaMemcpy(max_k_host, reinterpret_cast<const int*>(workspace) + 1, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { mh_set_error("mh_voxel_fuse_max_points: %s", cudaGetErrorString(e)); return 2; }
     return 0;
 }
 

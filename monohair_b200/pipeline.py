@@ -116,16 +116,10 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
         return o, l
     nbr = knn_stage(pts, pts, k, dev)
     filt = head_filter_stage(pm, pts, pm.visible_threshold).to(torch.uint8).contiguous()
+    scratch = torch.empty((sub_num, 4), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        st = stream_ptr(dev)
-        for i in range(n // sub_num + 1):
-            a, b = i * sub_num, min((i + 1) * sub_num, n)
-            if b <= a:
-                continue
-            center = P.medoid_gather(o, nbr[a:b], dev)
-            upd = pm.refine_loss_raw(pts[a:b], center)
-            check(lib().mh_refine_update(st, ptr(center), ptr(upd), ptr(filt[a:b]), b - a, ptr(o[a:b]), ptr(l[a:b])),
-                  "mh_refine_update")
+        check(lib().mh_refine_chunks(stream_ptr(dev), pm._vp(), ptr(pts), ptr(nbr), k, ptr(filt), n, sub_num,
+                                     float(pm.conf_threshold), ptr(o), ptr(l), ptr(scratch)), "mh_refine_chunks")
     return o, l
 
 
@@ -172,8 +166,9 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
         fo, fp = center[~fh], fu[~fh]
     else:
         fo, fp = so.new_zeros((0, 3)), so.new_zeros((0, 3))
+    all_p, all_o = torch.cat([sp, fp], 0), torch.cat([so, fo], 0)
     mark("unvisible")
-    vol = fuse_stage(pm, torch.cat([sp, fp], 0), torch.cat([so, fo], 0))
+    vol = fuse_stage(pm, all_p, all_o)
     mark("fuse")
     out = {"volume": vol, "surface": surface, "filter": filt, "select_p": pts, "select_o": ori, "min_loss": loss,
            "high_conf": hc, "refine_o": o2, "refine_loss": l2, "fu_points": fp, "fu_ori": fo,
