@@ -148,8 +148,7 @@ int64_t mh_voxel_fuse_workspace_bytes(int64_t n_points, int32_t gx, int32_t gy, 
 int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
                   const double* voxel_min_host /*[3]*/, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
                   void* volume /*float4 [gz][gy][gx]*/, int32_t* vox_index, void* workspace, int64_t workspace_bytes);
-/* Synchronous: largest per-voxel point count seen by the last mh_voxel_fuse on this workspace (voxels holding
- * more than 1024 points are fused from 1024 of them; the host raises if that ever happens). */
+/* Synchronous: largest per-voxel point count seen by the last mh_voxel_fuse on this workspace (informational). */
 int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host);
 /* Overwrite voxels with given orientations, last writer wins (raw.npy merge, PMVO.py:747-749). */
 int mh_voxel_overwrite(void* stream, const float* points, const float* dirs, int64_t n,

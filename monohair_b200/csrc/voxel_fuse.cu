@@ -36,11 +36,11 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, 
     if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
 }
 
-// Pass 1: voxel key of every point and a per-voxel linked list threaded through next[]; the list head lives in the
-// (zeroed) volume itself, in the .w slot of the voxel's float4, as the integer id+1 of the last point inserted.
+// Pass 1 (per point): voxel key, arrival rank inside the voxel (atomic count in a dense int32 plane), and the first
+// arrival of each voxel registers it in the compact list of occupied voxels.
 __global__ void __launch_bounds__(256)
-link_kernel(VGrid g, const float* __restrict__ pts, int64_t n, float4* __restrict__ volume, int* __restrict__ next,
-            int* __restrict__ key, int* __restrict__ vox_index) {
+count_kernel_vf(VGrid g, const float* __restrict__ pts, int64_t n, int* __restrict__ cnt, int* __restrict__ key,
+                int* __restrict__ rank, int* __restrict__ occ_list, int* __restrict__ hdr, int* __restrict__ vox_index) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int x, y, z;
@@ -48,113 +48,122 @@ link_kernel(VGrid g, const float* __restrict__ pts, int64_t n, float4* __restric
     const int k = (z * g.gy + y) * g.gx + x;
     key[i] = k;
     if (vox_index) vox_index[i] = (x * g.gy + y) * g.gz + z;
-    next[i] = atomicExch(reinterpret_cast<int*>(volume + k) + 3, (int)i + 1);
+    const int r = atomicAdd(cnt + k, 1);
+    rank[i] = r;
+    if (r == 0) occ_list[atomicAdd(hdr, 1)] = k;
 }
 
-// Pass 2: the point that is its voxel's list head resolves the voxel.  Up to 4 points are handled in registers
-// (ids sorted back into original order, medoid under |cos| -- for K <= 4 torch.mean's order is the plain sequential
-// sum); larger voxels go to a work list for the warp-per-voxel kernel.
+// Pass 2 (per occupied voxel): reserve a bucket [base, base+count) (any disjoint placement will do, so a plain atomic
+// cursor replaces a scan); the dense plane now holds the bucket base.
 __global__ void __launch_bounds__(256)
-head_kernel(int64_t n, const int* __restrict__ key, const int* __restrict__ next, const float* __restrict__ dirs,
-            float4* __restrict__ volume, int* __restrict__ worklist, int* __restrict__ wl_count, int* __restrict__ max_k) {
+bucket_kernel(const int* __restrict__ occ_list, int* __restrict__ cnt, int* __restrict__ cnt_list, int* __restrict__ hdr) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= hdr[0]) return;
+    const int k = occ_list[j];
+    const int c = cnt[k];
+    cnt_list[j] = c;
+    cnt[k] = atomicAdd(hdr + 2, c);
+    atomicMax(hdr + 1, c);
+}
+
+// Pass 3 (per point): drop the point id into its voxel's bucket.
+__global__ void __launch_bounds__(256)
+scatter_kernel(int64_t n, const int* __restrict__ key, const int* __restrict__ rank, const int* __restrict__ cnt,
+               int* __restrict__ bucket) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int k = key[i];
-    if (__float_as_int(volume[k].w) != (int)i + 1) return;
-    int id[4] = {0, 0, 0, 0};
-    int cnt = 0;
-    for (int j = (int)i + 1; j != 0; j = next[j - 1]) { if (cnt < 4) id[cnt] = j - 1; ++cnt; }
-    if (cnt > 4) {
-        worklist[atomicAdd(wl_count, 1)] = k;
-        atomicMax(max_k, cnt);
-        return;
-    }
-    // sort ids ascending (original point order decides argmax ties)
-    for (int a = 1; a < cnt; ++a) for (int b = a; b > 0 && id[b - 1] > id[b]; --b) { const int t_ = id[b]; id[b] = id[b - 1]; id[b - 1] = t_; }
-    float u[4][3], raw[4][3];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        if (a < cnt) {
-            load_dir(dirs, id[a], raw[a][0], raw[a][1], raw[a][2]);
-            const float nn = fmaxf(mh_norm3(raw[a][0], raw[a][1], raw[a][2]), 1e-8f);
-            u[a][0] = raw[a][0] / nn; u[a][1] = raw[a][1] / nn; u[a][2] = raw[a][2] / nn;
-        } else { u[a][0] = u[a][1] = u[a][2] = raw[a][0] = raw[a][1] = raw[a][2] = 0.0f; }
-    }
-    int bk = 0;
-    if (cnt > 1) {
-        float best = -1e30f;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            if (a < cnt) {
-                float sum = 0.0f;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (b < cnt) sum += fabsf((u[a][0] * u[b][0] + u[a][1] * u[b][1]) + u[a][2] * u[b][2]);
-                sum = sum / (float)cnt;
-                if (sum > best) { best = sum; bk = a; }
-            }
-        }
-    }
-    float o0 = raw[0][0], o1 = raw[0][1], o2 = raw[0][2];
-#pragma unroll
-    for (int a = 1; a < 4; ++a) if (bk == a) { o0 = raw[a][0]; o1 = raw[a][1]; o2 = raw[a][2]; }
-    volume[k] = make_float4(o0, -o1, -o2, 1.0f);
+    bucket[cnt[key[i]] + rank[i]] = (int)i;
 }
 
-// Pass 3: one warp per voxel with more than 4 points: ids gathered from the list, rank-sorted into original order,
-// medoid under |cos| with torch.mean's summation order (compute_points_similarity, PMVO_utils.py:366-382).
-constexpr int FUSE_WARPS = 4, FUSE_MAXK = 1024;
+// Pass 4: one warp per occupied voxel.  Bucket ids are rank-sorted back into original point order (argmax ties go
+// to the first point) and the medoid under |cos| is taken with torch.mean's summation order
+// (compute_points_similarity, PMVO_utils.py:366-382).  K <= FUSE_FASTK stays in shared memory; larger voxels use the
+// global scratch `sorted` (rare).
+constexpr int FUSE_WARPS = 8, FUSE_FASTK = 64;
 
 __global__ void __launch_bounds__(FUSE_WARPS * 32)
-fuse_medoid_kernel(const int* __restrict__ worklist, const int* __restrict__ wl_count, const int* __restrict__ next,
+fuse_medoid_kernel(const int* __restrict__ occ_list, const int* __restrict__ cnt_list, const int* __restrict__ cnt,
+                   const int* __restrict__ hdr, const int* __restrict__ bucket, int* __restrict__ sorted,
                    const float* __restrict__ dirs, float4* __restrict__ volume) {
-    extern __shared__ __align__(16) unsigned char fm_smem[];
+    __shared__ int s_idx_all[FUSE_WARPS][FUSE_FASTK];
+    __shared__ float s_u_all[FUSE_WARPS][FUSE_FASTK * 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* s_raw = reinterpret_cast<int*>(fm_smem) + (size_t)warp * FUSE_MAXK * 5;      // [MAXK] unsorted ids
-    int* s_idx = s_raw + FUSE_MAXK;                                                  // [MAXK] sorted ids
-    float* u = reinterpret_cast<float*>(s_idx + FUSE_MAXK);                           // [MAXK][3]
-    const int nwl = *wl_count;
-    for (int w = blockIdx.x * FUSE_WARPS + warp; w < nwl; w += gridDim.x * FUSE_WARPS) {
-        const int g = worklist[w];
-        int K = 0;
-        if (lane == 0) {
-            for (int j = __float_as_int(volume[g].w); j != 0 && K < FUSE_MAXK; j = next[j - 1]) s_raw[K++] = j - 1;
-        }
-        K = __shfl_sync(0xffffffffu, K, 0);
-        __syncwarp();
-        for (int a = lane; a < K; a += 32) {
-            const int v = s_raw[a];
-            int rank = 0;
-            for (int b = 0; b < K; ++b) rank += (s_raw[b] < v) ? 1 : 0;
-            s_idx[rank] = v;
-        }
-        __syncwarp();
-        for (int a = lane; a < K; a += 32) {
-            float a0, a1, a2;
-            load_dir(dirs, s_idx[a], a0, a1, a2);
-            const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
-            u[3 * a] = a0 / na; u[3 * a + 1] = a1 / na; u[3 * a + 2] = a2 / na;
-        }
-        __syncwarp();
-        float best = -1e30f; int bk = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
-            const float a0 = u[3 * k], a1 = u[3 * k + 1], a2 = u[3 * k + 2];
-            float sum = mh_torch_inner_sum(K, [&](int j) { return fabsf((a0 * u[3 * j] + a1 * u[3 * j + 1]) + a2 * u[3 * j + 2]); });
-            sum = sum / (float)K;
-            if (sum > best) { best = sum; bk = k; }
-        }
+    const int M = hdr[0];
+    for (int j = blockIdx.x * FUSE_WARPS + warp; j < M; j += gridDim.x * FUSE_WARPS) {
+        const int g = occ_list[j];
+        const int K = cnt_list[j], base = cnt[g];
+        int bk = 0, best_id;
+        if (K == 1) {
+            best_id = bucket[base];
+        } else if (K <= FUSE_FASTK) {
+            int* s_idx = s_idx_all[warp];
+            float* u = s_u_all[warp];
+            for (int a = lane; a < K; a += 32) {
+                const int v = bucket[base + a];
+                int rank = 0;
+                for (int b = 0; b < K; ++b) rank += (bucket[base + b] < v) ? 1 : 0;
+                s_idx[rank] = v;
+            }
+            __syncwarp();
+            for (int a = lane; a < K; a += 32) {
+                float a0, a1, a2;
+                load_dir(dirs, s_idx[a], a0, a1, a2);
+                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
+                u[3 * a] = a0 / na; u[3 * a + 1] = a1 / na; u[3 * a + 2] = a2 / na;
+            }
+            __syncwarp();
+            float best = -1e30f; bk = 0x7fffffff;
+            for (int k = lane; k < K; k += 32) {
+                const float a0 = u[3 * k], a1 = u[3 * k + 1], a2 = u[3 * k + 2];
+                float sum = mh_torch_inner_sum(K, [&](int t) { return fabsf((a0 * u[3 * t] + a1 * u[3 * t + 1]) + a2 * u[3 * t + 2]); });
+                sum = sum / (float)K;
+                if (sum > best) { best = sum; bk = k; }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+            }
+            best_id = s_idx[bk];
+            __syncwarp();
+        } else {
+            // crowded voxel: same algorithm through global memory
+            for (int a = lane; a < K; a += 32) {
+                const int v = bucket[base + a];
+                int rank = 0;
+                for (int b = 0; b < K; ++b) rank += (bucket[base + b] < v) ? 1 : 0;
+                sorted[base + rank] = v;
+            }
+            __syncwarp();
+            float best = -1e30f; bk = 0x7fffffff;
+            for (int k = lane; k < K; k += 32) {
+                float a0, a1, a2;
+                load_dir(dirs, sorted[base + k], a0, a1, a2);
+                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
+                a0 = a0 / na; a1 = a1 / na; a2 = a2 / na;
+                float sum = mh_torch_inner_sum(K, [&](int t) {
+                    float b0, b1, b2;
+                    load_dir(dirs, sorted[base + t], b0, b1, b2);
+                    const float nb = fmaxf(mh_norm3(b0, b1, b2), 1e-8f);
+                    return fabsf((a0 * (b0 / nb) + a1 * (b1 / nb)) + a2 * (b2 / nb)); });
+                sum = sum / (float)K;
+                if (sum > best) { best = sum; bk = k; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+            }
+            best_id = sorted[base + bk];
+            __syncwarp();
         }
         if (lane == 0) {
             float o0, o1, o2;
-            load_dir(dirs, s_idx[bk], o0, o1, o2);
+            load_dir(dirs, best_id, o0, o1, o2);
             volume[g] = make_float4(o0, -o1, -o2, 1.0f);
         }
-        __syncwarp();
     }
 }
 
@@ -228,11 +237,27 @@ VGrid make_grid(const double* vmin, double vs, int gx, int gy, int gz) {
 
 }  // namespace
 
-// workspace: [hdr 64 B: wl_count, max_k][next n][key n][worklist n/5+4]
+// workspace: [hdr 64 B: #occupied, max count, bucket cursor][cnt nvox][key n][rank n][occ_list n][cnt_list n][bucket n][sorted n]
 extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
-    (void)gx; (void)gy; (void)gz;
-    return 64 + 4 * (2 * n + n / 5 + 8);
+    const int64_t nvox = (int64_t)gx * gy * gz;
+    return 64 + 4 * (nvox + 6 * n + 16);
 }
+
+namespace {
+struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+AuxStream& aux_stream() {
+    static thread_local AuxStream a[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    AuxStream& x = a[dev & 15];
+    if (!x.s) {
+        cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
+    }
+    return x;
+}
+}  // namespace
 
 extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
                              const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
@@ -245,30 +270,46 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
     const int64_t nvox = (int64_t)gx * gy * gz;
     const VGrid g = make_grid(voxel_min_host, voxel_size, gx, gy, gz);
     int* hdr = reinterpret_cast<int*>(workspace);
-    int* next = hdr + 16;
-    int* key = next + n;
-    int* worklist = key + n;
+    int* cnt = hdr + 16;
+    int* key = cnt + nvox;
+    int* rank = key + n;
+    int* occ_list = rank + n;
+    int* cnt_list = occ_list + n;
+    int* bucket = cnt_list + n;
+    int* sorted = bucket + n;
+    // The 16 B/voxel zero fill of the volume (the bandwidth-bound part) runs on an auxiliary stream, concurrently
+    // with the latency-bound bucket construction; the two join before the per-voxel results are written.
+    AuxStream& ax = aux_stream();
+    cudaEventRecord(ax.fork, st);
+    cudaStreamWaitEvent(ax.s, ax.fork, 0);
+    cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, ax.s);
+    cudaEventRecord(ax.join, ax.s);
     cudaMemsetAsync(hdr, 0, 64, st);
-    cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, st);            // empty voxels: the streaming 16 B/voxel write
-    if (n == 0) return 0;
-    link_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, points, n, reinterpret_cast<float4*>(volume), next, key, vox_index);
-    MH_COUNT_LAUNCH();
-    head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, key, next, dirs, reinterpret_cast<float4*>(volume), worklist, hdr, hdr + 1);
-    MH_COUNT_LAUNCH();
-    const size_t smem = (size_t)FUSE_WARPS * FUSE_MAXK * 5 * sizeof(int);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(fuse_medoid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    int64_t blocks = (n / 5 + FUSE_WARPS) / FUSE_WARPS;
-    const int64_t cap = (int64_t)mh_sm_count() * 2;
-    if (blocks > cap) blocks = cap;
-    fuse_medoid_kernel<<<(unsigned)blocks, FUSE_WARPS * 32, smem, st>>>(worklist, hdr, next, dirs, reinterpret_cast<float4*>(volume));
-    MH_COUNT_LAUNCH();
+    if (n > 0) {
+        cudaMemsetAsync(cnt, 0, sizeof(int) * nvox, st);
+        const unsigned nb = (unsigned)((n + 255) / 256);
+        count_kernel_vf<<<nb, 256, 0, st>>>(g, points, n, cnt, key, rank, occ_list, hdr, vox_index);
+        MH_COUNT_LAUNCH();
+        bucket_kernel<<<nb, 256, 0, st>>>(occ_list, cnt, cnt_list, hdr);
+        MH_COUNT_LAUNCH();
+        scatter_kernel<<<nb, 256, 0, st>>>(n, key, rank, cnt, bucket);
+        MH_COUNT_LAUNCH();
+    }
+    cudaStreamWaitEvent(st, ax.join, 0);
+    if (n > 0) {
+        int64_t blocks = (n + FUSE_WARPS - 1) / FUSE_WARPS;
+        const int64_t cap = (int64_t)mh_sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        fuse_medoid_kernel<<<(unsigned)blocks, FUSE_WARPS * 32, 0, st>>>(occ_list, cnt_list, cnt, hdr, bucket, sorted, dirs,
+                                                                        reinterpret_cast<float4*>(volume));
+        MH_COUNT_LAUNCH();
+    }
     MH_CHECK_LAUNCH();
     return 0;
 }
 
 /* after synchronising the stream: the largest number of points that fell into one voxel in the last mh_voxel_fuse
- * call on this workspace; voxels with more than 1024 points are fused from their first 1024 (in list order). */
+ * call on this workspace (informational: crowded voxels take the global-memory path of fuse_medoid_kernel). */
 extern "C" int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host) {
     MH_CHECK_ARG(workspace && max_k_host, "null pointer");
     cudaError_t e = cudaMemcpy(max_k_host, reinterpret_cast<const int*>(workspace) + 1, 4, cudaMemcpyDeviceToHost);

@@ -362,8 +362,7 @@ def medoid_gather(ori, nbr, dev):
     return out
 
 
-def voxel_fuse(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, voxel_size=VOXEL_SIZE, return_index=False,
-               check_crowding=True):
+def voxel_fuse(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, voxel_size=VOXEL_SIZE, return_index=False):
     """PMVO.py:695-726 on the device -> float4 volume [gz,gy,gx,4] (see include/monohair_b200.h)."""
     pts = torch.as_tensor(select_points).to(dev).type(torch.float).contiguous()
     dirs = torch.as_tensor(select_ori).to(dev).type(torch.float).contiguous()
@@ -377,11 +376,6 @@ def voxel_fuse(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, v
     with torch.cuda.device(dev):
         check(lib().mh_voxel_fuse(stream_ptr(dev), ptr(pts), ptr(dirs), n, vmin.ctypes.data_as(C.c_void_p),
                                   float(voxel_size), gx, gy, gz, ptr(vol), ptr(vidx), ptr(ws), wsb), "mh_voxel_fuse")
-        if check_crowding:
-            mk = C.c_int32(0)
-            check(lib().mh_voxel_fuse_max_points(ptr(ws), C.byref(mk)), "mh_voxel_fuse_max_points")
-            if mk.value > 1024:
-                raise _lib.MonoHairError(f"a voxel received {mk.value} points; more than 1024 per voxel is not supported")
     return (vol, vidx) if return_index else vol
 
 

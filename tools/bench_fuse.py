@@ -1,0 +1,52 @@
+"""Micro-benchmark of mh_voxel_fuse on shell-like points (for ncu and for the HBM roofline of the fusion kernels)."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from monohair_b200 import synthetic as syn  # noqa: E402
+from monohair_b200 import pmvo as P  # noqa: E402
+from monohair_b200._lib import check, lib, ptr, stream_ptr  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda:0")
+    cand = syn.candidate_points(num_per_grid=4, seed=0)
+    rng = np.random.default_rng(0)
+    sel = cand[rng.random(cand.shape[0]) < 0.84]
+    pts = torch.from_numpy(sel).to(dev).float().contiguous()
+    dirs = syn.flow_tangent(pts.double(), syn.RADII).float().contiguous()
+    n = pts.size(0)
+    gx, gy, gz = P.GRID
+    vol = torch.empty((gz, gy, gx, 4), dtype=torch.float32, device=dev)
+    wsb = lib().mh_voxel_fuse_workspace_bytes(n, gx, gy, gz)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    vmin = np.ascontiguousarray(P.VOXEL_MIN)
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+
+    def run():
+        check(lib().mh_voxel_fuse(stream_ptr(dev), ptr(pts), ptr(dirs), n, vmin.ctypes.data_as(C.c_void_p), float(P.VOXEL_SIZE),
+                                  gx, gy, gz, ptr(vol), None, ptr(ws), wsb), "mh_voxel_fuse")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()                                  # flush L2 (126 MB) between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    nvox = gx * gy * gz
+    alg = n * 28 + n * 16 + nvox * 16
+    occ = int(vol[..., 3].sum().item())
+    print(f"voxel_fuse: n={n} occupied={occ} median {ms*1e3:.1f} us  algorithmic {alg/1e6:.1f} MB -> {alg/ms/1e6:.0f} GB/s")
+
+
+if __name__ == "__main__":
+    main()
