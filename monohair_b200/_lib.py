@@ -10,7 +10,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmonohair_b200.so")
+LIB_PATH = os.environ.get("MH_LIB") or os.path.join(HERE, "libmonohair_b200.so")   # MH_LIB: tuning experiments only
 
 MH_CAM_STRIDE = 32
 MH_TOPK = 20

@@ -25,10 +25,11 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    if out is None and not force and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT] + sources()
+    out = out or OUT
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
@@ -38,7 +39,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libmonohair_b200.so")
     if verbose:
         print(log)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

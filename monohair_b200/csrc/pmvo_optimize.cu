@@ -24,7 +24,10 @@
 
 namespace {
 
-constexpr int OPT_WARPS = 5;
+#ifndef OPT_WARPS_N
+#define OPT_WARPS_N 5
+#endif
+constexpr int OPT_WARPS = OPT_WARPS_N;
 constexpr int OPT_THREADS = 32 * OPT_WARPS;
 #ifndef OPT_MIN_BLOCKS
 #define OPT_MIN_BLOCKS 4

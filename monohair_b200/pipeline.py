@@ -18,6 +18,7 @@ from . import pmvo as P
 from ._lib import check, lib, ptr, stream_ptr
 
 
+_PINNED = {}               # reusable pinned result buffers of pmvo_job_host (the caller must consume them before the next call)
 _FORCE_SINGLE = False      # tests: run the single-GPU path inside a multi-rank process
 
 
@@ -191,6 +192,15 @@ def pmvo_job_host(camera, depths, Ori, Conf, masks, candidates_host, image_size,
                     visible_threshold=visible_threshold, conf_threshold=conf_threshold)
     cand = torch.as_tensor(candidates_host).to(device, non_blocking=True).type(torch.float).contiguous()
     out = pmvo_job_device(pm, cand, threshold)
-    host = {k: out[k].cpu() for k in ("volume", "select_o", "min_loss", "high_conf")}
+    host = {}
+    for k in ("volume", "select_o", "min_loss", "high_conf"):
+        t = out[k]
+        key = (k, tuple(t.shape), t.dtype)
+        if key not in _PINNED:
+            _PINNED.clear() if len(_PINNED) > 16 else None
+            _PINNED[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        _PINNED[key].copy_(t, non_blocking=True)
+        host[k] = _PINNED[key]
+    torch.cuda.current_stream(torch.device(device)).synchronize()
     host["n_optimized"] = out["n_optimized"]
     return host
