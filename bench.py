@@ -254,13 +254,15 @@ def run_b200(args, cfg):
     opt_bytes = n_opt_local * cfg["V"] * (PP * 12 + 4 + 4 + 8 + 4)              # 608 B per (point, view) at P=7
     n_cov = stats["n_candidates"] // 30 * (30 if stats["n_candidates"] % 30 == 0 else 31)
     n_cov = min(n_cov, stats["n_candidates"])
-    filt_bytes = ((n_cov + world - 1) // world) * (cfg["V"] * (4 + 4 + 4 * PP) + 12 + 3)   # reference fp32 maps: 204 B per (point, view)
+    # filter_points: what this implementation has to read per (point, view) = 8 B {depth, mask'} + 4 B (PxP max conf);
+    # + 12 B point + 20 B counters per point.  (The reference's own formulation gathers 204 B per pair)
+    filt_bytes = ((n_cov + world - 1) // world) * (cfg["V"] * 12 + 12 + 20)
     n_fused = stats["n_selected"] + stats["n_fu"]
     nvox = 256 * 256 * 192
     fuse_bytes = n_fused * 28 + n_fused * 2 * 8 + nvox * 16                      # SURVEY §8d voxel fusion
     roofline = {"bound": "hbm", "kernel": "optimize_kernel (PMVO.forward, FP32-ALU bound by design: SURVEY.md §8d)",
                 "achieved": opt_bytes / (med["optimize"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": opt_bytes / (med["optimize"] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": opt_bytes / (med["optimize"] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "ms": med["optimize"],
                 "hbm_bound_kernels": {
                     "voxel_fuse": {"achieved": fuse_bytes / (med["fuse"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
