@@ -260,6 +260,13 @@ def run_b200(args, cfg):
     n_fused = stats["n_selected"] + stats["n_fu"]
     nvox = 256 * 256 * 192
     fuse_bytes = n_fused * 28 + n_fused * 2 * 8 + nvox * 16                      # SURVEY §8d voxel fusion
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["optimize_kernel"]
+        if tr["workload"] == cfg["name"] and tr["dram_bytes_per_launch"]:
+            traffic = tr["dram_bytes_per_launch"] * (n_opt_local / tr["points_per_launch"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "optimize_kernel (PMVO.forward, FP32-ALU bound by design: SURVEY.md §8d)",
                 "achieved": opt_bytes / (med["optimize"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": opt_bytes / (med["optimize"] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
