@@ -139,12 +139,6 @@ int mh_refine_chunks(void* stream, const mh_views* views, const float* points, c
                      const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
                      float* ori /*in/out*/, float* loss /*out*/, float* scratch /*[sub_num][4] floats*/);
 
-/* Same pass with ONE fused kernel per chunk (256 threads per point: medoid, re-score with 4 threads per view,
- * update staged in scratch and committed after the chunk) -- the default; K <= 256. */
-int mh_refine_chunks_fused(void* stream, const mh_views* views, const float* points, const int32_t* nbr, int32_t K,
-                           const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
-                           float* ori /*in/out*/, float* loss /*out*/, float* scratch /*[sub_num][3] floats*/);
-
 /* ---- voxel fusion (PMVO.py:695-726, PMVO_utils.p2v :386-404) ------------------------------------------ */
 int64_t mh_voxel_fuse_workspace_bytes(int64_t n_points, int32_t gx, int32_t gy, int32_t gz);
 /* points float32 [n][3] (world), dirs float32 [n][3].  Flips dirs to dir.y<=0 (PMVO.py:702-703), voxelises with

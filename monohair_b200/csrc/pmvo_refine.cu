@@ -662,191 +662,3 @@ extern "C" int mh_refine_chunks(void* stream, const mh_views* vw, const float* p
     }
     return 0;
 }
-
-// ---- fused chunk kernel: medoid -> re-score -> staged update, one CTA per point ------------------------------
-// The per-chunk launches of PMVO.refine step (i) are small (5000 points) and strictly ordered, so they are
-// latency-bound.  This kernel spends 256 threads per point: phase 1 takes the medoid of the K neighbour
-// orientations (one candidate per thread, torch.mean order), phase 2 scores next = p + center*0.00125 against every
-// view with 4 threads per view (each loads its quarter of the PxP patch in one go; the reference's sequential scan
-// is a first-index minimum over {entry 0} U eligible entries, so it splits exactly), phase 3 applies the cascade sum
-// and the update rule.  Updated orientations are staged in `ori_new` and committed by refine_commit_kernel after the
-// whole chunk has read the old values (Jacobi inside a chunk, Gauss-Seidel across chunks, as in the reference).
-namespace {
-constexpr int RC_THREADS = 256, RC_MAXK = 256, RC_PARTS = 4;
-
-__global__ void __launch_bounds__(RC_THREADS, 4)
-refine_chunk_kernel(mh_views vw, const float* __restrict__ pts, const int32_t* __restrict__ nbr, int K,
-                    const uint8_t* __restrict__ head_filter, float thr_c, const float* __restrict__ ori, int64_t base,
-                    float* __restrict__ ori_new, float* __restrict__ loss) {
-    extern __shared__ __align__(16) unsigned char rc_smem[];
-    float* u = reinterpret_cast<float*>(rc_smem);                 // [K][3] normalised neighbour orientations
-    float* lw = u + 3 * RC_MAXK;                                  // [V][2]
-    float* red_v = lw + 2 * vw.V;                                 // [8]
-    int* red_i = reinterpret_cast<int*>(red_v + 8);               // [8]
-    float* cen = reinterpret_cast<float*>(red_i + 8);             // [4] center (raw) 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t i = blockIdx.x;
-    const int V = vw.V, P = vw.P, half = P / 2, PP = P * P;
-
-    // ---- phase 1: medoid of the neighbours' current orientations (compute_points_similarity) ----
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-    if (tid < K) {
-        const int r = nbr[i * K + tid];
-        r0 = ori[3 * r]; r1 = ori[3 * r + 1]; r2 = ori[3 * r + 2];
-        const float nn = fmaxf(mh_norm3(r0, r1, r2), 1e-8f);
-        u[3 * tid] = r0 / nn; u[3 * tid + 1] = r1 / nn; u[3 * tid + 2] = r2 / nn;
-    }
-    __syncthreads();
-    float best = -1e30f; int bk = 0x7fffffff;
-    if (tid < K) {
-        const float a = u[3 * tid], b = u[3 * tid + 1], c = u[3 * tid + 2];
-        float s = mh_torch_inner_sum(K, [&](int j) { return fabsf((a * u[3 * j] + b * u[3 * j + 1]) + c * u[3 * j + 2]); });
-        best = s / (float)K;
-        bk = tid;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-        if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
-    }
-    if (lane == 0) { red_v[warp] = best; red_i[warp] = bk; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < RC_THREADS / 32; ++w)
-            if (red_v[w] > best || (red_v[w] == best && red_i[w] < bk)) { best = red_v[w]; bk = red_i[w]; }
-        red_i[0] = bk;
-    }
-    __syncthreads();
-    bk = red_i[0];
-    if (tid == bk) { cen[0] = r0; cen[1] = r1; cen[2] = r2; }     // the medoid's raw orientation
-    __syncthreads();
-    const float c0 = cen[0], c1 = cen[1], c2 = cen[2];
-
-    // ---- phase 2: single-sample reprojection loss of (p, p + center*0.005/4), 4 threads per view ----
-    const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
-    const float qx = px + c0 * 0.005f / 4.0f, qy = py + c1 * 0.005f / 4.0f, qz = pz + c2 * 0.005f / 4.0f;
-    const float Wf = (float)vw.W, Hf = (float)vw.H;
-    const size_t plane = (size_t)vw.H * vw.W;
-    const int part = tid % RC_PARTS;
-    for (int v0 = 0; v0 < V; v0 += RC_THREADS / RC_PARTS) {
-        const int v = v0 + tid / RC_PARTS;
-        float bl = 0.0f, bc = 0.0f; int bp = 0x7fffffff;
-        bool visv = false, seed_nan = false;
-        if (v < V) {
-            const MhCam cm = *reinterpret_cast<const MhCam*>(vw.cam + (size_t)v * MH_CAM_STRIDE);
-            float cx, cy, cz, xp, yp;
-            mh_world_to_cam(cm.p, px, py, pz, cx, cy, cz);
-            mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, cx, cy, cz, xp, yp);
-            int row, col; bool oob;
-            mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
-            const float4* __restrict__ mp = reinterpret_cast<const float4*>(vw.mapP) + (size_t)v * plane;
-            const float2 dm = __ldg(reinterpret_cast<const float2*>(vw.mapC) + (size_t)v * plane + (size_t)row * vw.W + col);
-            float vis = mh_visible((-cz / 2.0f) * 255.0f, dm.x);
-            if (oob) vis = -1.0f;
-            visv = vis != -1.0f;
-            if (visv) {
-                float c2x, c2y, c2z, xs, ys, y0, y1;
-                mh_world_to_cam(cm.p, qx, qy, qz, c2x, c2y, c2z);
-                mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, c2x, c2y, c2z, xs, ys);
-                mh_normalize2(ys - yp, xs - xp, y0, y1);
-                const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mp + (size_t)row * vw.W + col) + 3), 1e-6f), 1.0f);
-                const bool hi = cmax > thr_c;
-                // this thread's slice of the patch, all loads first
-                const int per = (PP + RC_PARTS - 1) / RC_PARTS;
-                const int pa = part * per, pb = min(PP, pa + per);
-                constexpr int MAXPER = (17 * 17 + RC_PARTS - 1) / RC_PARTS;
-                float4 t[8];
-                for (int p0 = pa; p0 < pb; p0 += 8) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int p = p0 + k;
-                        if (p < pb) {
-                            const int di = p / P - half, dj = p % P - half;
-                            t[k] = __ldg(mp + (size_t)min(max(row + di, 0), vw.H - 1) * vw.W + min(max(col + dj, 0), vw.W - 1));
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int p = p0 + k;
-                        if (p < pb) {
-                            float x0, x1;
-                            mh_normalize2(t[k].x, t[k].y, x0, x1);
-                            const float cf = fminf(fmaxf(t[k].z, 1e-6f), 1.0f);
-                            const float l = 1.0f - fabsf(x0 * y0 + x1 * y1);
-                            if (p == 0) { bl = l; bc = cf; bp = 0; seed_nan = l != l; }
-                            else if ((!hi || cf > thr_c) && l == l && (bp == 0x7fffffff || l < bl)) { bl = l; bc = cf; bp = p; }
-                        }
-                    }
-                }
-                (void)MAXPER;
-            }
-        }
-        // combine the 4 parts: smallest loss, first index on ties; a NaN seed (entry 0) sticks like in the scan
-#pragma unroll
-        for (int o = 1; o < RC_PARTS; o <<= 1) {
-            const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
-            const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
-            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-            const bool osn = __shfl_xor_sync(0xffffffffu, (int)seed_nan, o) != 0;
-            bool take;
-            if (seed_nan) take = false;
-            else if (osn) take = true;
-            else take = op != 0x7fffffff && (bp == 0x7fffffff || ol < bl || (ol == bl && op < bp));
-            if (take) { bl = ol; bc = oc; bp = op; }
-            seed_nan = seed_nan || osn;
-        }
-        if (v < V && part == 0) { lw[2 * v] = visv ? bl * bc : 0.0f; lw[2 * v + 1] = visv ? bc : 0.0f; }
-    }
-    __syncthreads();
-
-    // ---- phase 3: view sums in torch.sum's cascade order, head filter, update rule (PMVO.py:92, 629-641) ----
-    if (tid == 0) {
-        MhCascade<2> acc;
-        acc.init(V);
-        for (int v = 0; v < V; ++v) {
-            if (lw[2 * v + 1] == 0.0f && lw[2 * v] == 0.0f) continue;
-            acc.begin_row(v);
-            acc.add(0, lw[2 * v]);
-            acc.add(1, lw[2 * v + 1]);
-        }
-        float s[2];
-        acc.finish(V, s);
-        float l = head_filter[i] ? -1.0f : s[0] / s[1];
-        if (l == -1.0f) l = 0.5f;
-        loss[i] = l;
-        const float o0 = ori[3 * (base + i)], o1 = ori[3 * (base + i) + 1], o2 = ori[3 * (base + i) + 2];
-        const float nc = fmaxf(mh_norm3(c0, c1, c2), 1e-8f), no = fmaxf(mh_norm3(o0, o1, o2), 1e-8f);
-        const float sim = fabsf(((c0 / nc) * (o0 / no) + (c1 / nc) * (o1 / no)) + (c2 / nc) * (o2 / no));
-        const bool ch = sim < 0.95f;
-        ori_new[3 * i] = ch ? c0 : o0; ori_new[3 * i + 1] = ch ? c1 : o1; ori_new[3 * i + 2] = ch ? c2 : o2;
-    }
-}
-
-__global__ void refine_commit_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n3) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n3) dst[i] = src[i];
-}
-}  // namespace
-
-extern "C" int mh_refine_chunks_fused(void* stream, const mh_views* vw, const float* points, const int32_t* nbr, int32_t K,
-                                      const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
-                                      float* ori, float* loss, float* scratch /* [sub_num][3] floats */) {
-    MH_CHECK_ARG(vw && points && nbr && head_filter && ori && loss && scratch, "null pointer");
-    MH_CHECK_ARG(sub_num > 0 && K >= 1 && K <= RC_MAXK && n >= 0, "bad arguments (K <= 256)");
-    MH_CHECK_ARG((vw->P & 1) && vw->P >= 1 && vw->P <= 17, "patch size must be odd and <= 17");
-    const size_t smem = sizeof(float) * (3 * RC_MAXK + 2 * vw->V + 8 + 8 + 4);
-    MH_CHECK_ARG(smem <= 48 * 1024, "too many views");
-    cudaStream_t st = (cudaStream_t)stream;
-    for (int64_t a = 0; a < n; a += sub_num) {
-        const int64_t m = (n - a < sub_num) ? (n - a) : sub_num;
-        // pointers are offset so that blockIdx.x indexes the chunk; nbr holds GLOBAL neighbour ids into `ori`
-        refine_chunk_kernel<<<(unsigned)m, RC_THREADS, smem, st>>>(*vw, points + 3 * a, nbr + a * K, K, head_filter + a,
-                                                                  conf_threshold, ori, a, scratch, loss + a);
-        MH_COUNT_LAUNCH();
-        refine_commit_kernel<<<(unsigned)((3 * m + 255) / 256), 256, 0, st>>>(scratch, ori + 3 * a, 3 * m);
-        MH_COUNT_LAUNCH();
-    }
-    MH_CHECK_LAUNCH();
-    return 0;
-}

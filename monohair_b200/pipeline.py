@@ -19,7 +19,6 @@ from ._lib import check, lib, ptr, stream_ptr
 
 
 _PINNED = {}               # reusable pinned result buffers of pmvo_job_host (the caller must consume them before the next call)
-_UNFUSED_REFINE = False    # tests: use the three-kernel chunk pass instead of the fused kernel
 _FORCE_SINGLE = False      # tests: run the single-GPU path inside a multi-rank process
 
 
@@ -120,9 +119,8 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
     filt = head_filter_stage(pm, pts, pm.visible_threshold).to(torch.uint8).contiguous()
     scratch = torch.empty((sub_num, 4), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        fn = lib().mh_refine_chunks_fused if (k <= 256 and not _UNFUSED_REFINE) else lib().mh_refine_chunks
-        check(fn(stream_ptr(dev), pm._vp(), ptr(pts), ptr(nbr), k, ptr(filt), n, sub_num,
-                 float(pm.conf_threshold), ptr(o), ptr(l), ptr(scratch)), "mh_refine_chunks")
+        check(lib().mh_refine_chunks(stream_ptr(dev), pm._vp(), ptr(pts), ptr(nbr), k, ptr(filt), n, sub_num,
+                                     float(pm.conf_threshold), ptr(o), ptr(l), ptr(scratch)), "mh_refine_chunks")
     return o, l
 
 

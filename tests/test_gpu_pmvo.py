@@ -200,25 +200,6 @@ def test_knn_exact_vs_kdtree():
     assert np.mean(idx == i_ref) > 0.9999
 
 
-def test_fused_and_unfused_refine_chunk_pass_identical(case):
-    from monohair_b200 import pipeline as PL
-    from monohair_b200 import pmvo as P
-    g, sc, pmvo = case
-    scalp = g["scalp"]
-    P.scalp_tree, P.scalp_max = KDTree(data=scalp), scalp.max(0)
-    pts = torch.from_numpy(g["fwd_points"].astype(np.float32)).cuda()
-    ori = torch.from_numpy(g["fwd_ori"]).cuda()
-    loss = torch.from_numpy(g["fwd_loss"]).cuda()
-    outs = []
-    for unfused in (False, True):
-        PL._UNFUSED_REFINE = unfused
-        try:
-            outs.append(PL.refine_stage(pmvo, pts, ori, loss, sub_num=77))       # several chunks: Gauss-Seidel order matters
-        finally:
-            PL._UNFUSED_REFINE = False
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-
-
 def test_knn_fallback_paths():
     """dense clumps (buffer overflow) and hundreds of coincident points (no separating radius) take the general
     kernel; results must still be the exact k nearest by distance."""
