@@ -333,7 +333,7 @@ def run_b200(args, cfg):
                            "grid": [256, 256, 192], "candidates": stats["n_candidates"], "optimised": n_opt,
                            "selected": stats["n_selected"], "near_surface": stats["n_fu"],
                            "cache": "inputs larger than L2 (%.1f GB of resident view maps, gathered)" %
-                                    ((cfg["V"] * cfg["H"] * cfg["W"] * 24) / 1e9),
+                                    ((cfg["V"] * cfg["H"] * cfg["W"] * 32) / 1e9),
                            "parallelism": "1 GPU" if world == 1 else f"points sharded over {world} GPUs + volume all-reduce"},
                 "stage_ms": med, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks}

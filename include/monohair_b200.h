@@ -29,8 +29,9 @@ extern "C" {
 /* Resident per-view maps (PMVO.__init__, PMVO.py:14-37).  All device pointers, owned by the caller. */
 typedef struct mh_views {
     int32_t V, H, W, P;        /* views, image rows, cols, patch size (odd) */
-    const void* mapC;          /* float2 [V][H][W] = {depth, mask'}   mask' = mask>0.2 ? 1 : mask  (PMVO.py:427) */
-    const void* mapP;          /* float4 [V][H][W] = {ori_row, ori_col, conf, max_{PxP} conf}      (PMVO.py:491-515) */
+    const void* mapC;          /* float4 [V][H][W] = {depth, mask', ori_row, ori_col}; mask' = mask>0.2 ? 1 : mask (PMVO.py:427) */
+    const void* mapP;          /* float4 [V][H][W] = {unit_row, unit_col, conf, max_{PxP} conf}: direction pre-normalised
+                                  as torch.cosine_similarity does (PMVO.py:171, 491-515) */
     const float* cam;          /* [V][MH_CAM_STRIDE] */
 } mh_views;
 
@@ -53,7 +54,7 @@ int mh_views_pack_camera_host(const float* pose_host, const float* ndc_prj_host,
 int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int32_t P,
                   const float* depth, int32_t depth_stride, const float* ori /*[H][W][2]*/,
                   const float* conf /*[H][W]*/, const float* mask, int32_t mask_stride,
-                  void* mapC /*[V][H][W] float2*/, void* mapP /*[V][H][W] float4*/);
+                  void* mapC /*[V][H][W] float4*/, void* mapP /*[V][H][W] float4*/);
 
 /* Same for the dtypes the reference's loaders produce (depth float32; Ori, Conf, mask float64): the float cast of
  * PMVO.py:23-26 is fused into the pack. */

@@ -3,8 +3,8 @@
 //   mh_visible_count                     PMVO.compute_unvisible_points (PMVO.py:461-480)
 //   mh_head_count                        PMVO.filter_head_points       (PMVO.py:110-136)
 // One thread per point, views in the outer loop so that all resident CTAs walk the views together and one
-// view's planes (mapC 8 B/px + the .w of mapP) stay L2-resident while they are being gathered.
-// Bound: L2/HBM gather bandwidth; algorithmic bytes per (point, view) = 8 (mapC) + 4 (max conf) = 12 B.
+// view's planes (mapC 16 B/px + the .w of mapP) stay L2-resident while they are being gathered.
+// Bound: L2/HBM gather bandwidth; algorithmic bytes per (point, view) = 8 ({depth, mask'} of mapC) + 4 (max conf) = 12 B.
 #include "mh_common.cuh"
 
 namespace {
@@ -25,7 +25,7 @@ count_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, float thr_v,
     constexpr int NC = (MODE == FILTER) ? 5 : (MODE == HEAD ? 2 : 1);
     MhCascade<NC> acc;
     acc.init(vw.V);
-    const float2* __restrict__ mapC = reinterpret_cast<const float2*>(vw.mapC);
+    const float4* __restrict__ mapC = reinterpret_cast<const float4*>(vw.mapC);
     const float4* __restrict__ mapP = reinterpret_cast<const float4*>(vw.mapP);
     const size_t plane = (size_t)vw.H * vw.W;
     const float Wf = (float)vw.W, Hf = (float)vw.H;
@@ -45,7 +45,7 @@ count_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, float thr_v,
             int row, col; bool oob;
             mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
             const size_t pix = (size_t)v * plane + (size_t)row * vw.W + col;
-            const float2 dm = __ldg(mapC + pix);
+            const float4 dm = __ldg(mapC + pix);
             const float delta = (-cz / 2.0f) * 255.0f - dm.x;
             if (MODE == FILTER) {
                 float cmax = __ldg(reinterpret_cast<const float*>(mapP + pix) + 3);
@@ -158,13 +158,13 @@ __global__ void centre_kernel(mh_views vw, const float* __restrict__ pts, int64_
     int row, col; bool oob;
     mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
     const size_t pix = (size_t)v * vw.H * vw.W + (size_t)row * vw.W + col;
-    const float2 dm = __ldg(reinterpret_cast<const float2*>(vw.mapC) + pix);
+    const float4 dm = __ldg(reinterpret_cast<const float4*>(vw.mapC) + pix);
     const float4 oc = __ldg(reinterpret_cast<const float4*>(vw.mapP) + pix);
     float vis = mh_visible((-cz / 2.0f) * 255.0f, dm.x);
     if (oob) vis = -1.0f;
     const size_t o = (size_t)v * N + n;
     visible[o] = vis;
-    ori[2 * o] = oc.x; ori[2 * o + 1] = oc.y;
+    ori[2 * o] = dm.z; ori[2 * o + 1] = dm.w;
     conf[o] = fminf(fmaxf(oc.z, 1e-6f), 1.0f);
     if (mask) mask[o] = dm.y;
     if (rowcol) { rowcol[2 * o] = row; rowcol[2 * o + 1] = oob ? -col - 1 : col; }

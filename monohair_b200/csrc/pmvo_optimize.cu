@@ -217,7 +217,7 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
     smem_layout(&sm, smem_raw, V, S, PP);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float Wf = (float)vw.W, Hf = (float)vw.H;
-    const float2* __restrict__ mapC = reinterpret_cast<const float2*>(vw.mapC);
+    const float4* __restrict__ mapC = reinterpret_cast<const float4*>(vw.mapC);
     const float4* __restrict__ mapP = reinterpret_cast<const float4*>(vw.mapP);
     const size_t plane = (size_t)vw.H * vw.W;
 
@@ -240,14 +240,14 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
             int row, col; bool oob;
             mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
             const int pix = row * vw.W + col;
-            const float2 dm = __ldg(mapC + (size_t)v * plane + pix);
+            const float4 dm = __ldg(mapC + (size_t)v * plane + pix);
             const float4 oc = __ldg(mapP + (size_t)v * plane + pix);
             float vis = mh_visible((-cz / 2.0f) * 255.0f, dm.x);
             if (oob) vis = -1.0f;
             const float conf = fminf(fmaxf(oc.z, 1e-6f), 1.0f);
             const float confp = (vis < 1.0f) ? conf * fmaxf(vis, 0.0f) : conf;      // :340
             sm.camz[v] = cz; sm.xp[v] = xp; sm.yp[v] = yp; sm.vis[v] = vis;
-            sm.orr[v] = oc.x; sm.orc[v] = oc.y; sm.pix[v] = pix;
+            sm.orr[v] = dm.z; sm.orc[v] = dm.w; sm.pix[v] = pix;
             sm.q[v].v = confp; sm.q[v].i = v;
         }
         __syncthreads();
@@ -286,7 +286,7 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
                         const int di = p / P - half, dj = p % P - half;                 // row offset outer (:494-500)
                         const int r = min(max(row + di, 0), vw.H - 1), c = min(max(col + dj, 0), vw.W - 1);
                         const float4 t = __ldg(mp + (size_t)r * vw.W + c);
-                        mh_normalize2(t.x, t.y, ex0, ex1);
+                        ex0 = t.x; ex1 = t.y;                                            // stored normalised (pmvo_views.cu)
                         ecf = fminf(fmaxf(t.z, 1e-6f), 1.0f);
                         elig = (p == 0) || !hi || (ecf > thr_c);
                         // duplicate of an entry already kept in an earlier 32-chunk?

@@ -29,7 +29,7 @@ refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __re
     __syncthreads();
     float* my = lw + (size_t)grp * V * 2;
     const float Wf = (float)vw.W, Hf = (float)vw.H;
-    const float2* __restrict__ mapC = reinterpret_cast<const float2*>(vw.mapC);
+    const float4* __restrict__ mapC = reinterpret_cast<const float4*>(vw.mapC);
     const float4* __restrict__ mapP = reinterpret_cast<const float4*>(vw.mapP);
     const size_t plane = (size_t)vw.H * vw.W;
     constexpr int MAXP = PT ? PT : 17;
@@ -50,7 +50,7 @@ refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __re
             int row, col; bool oob;
             mh_round_clamp(xp, yp, vw.W, vw.H, row, col, oob);
             const float4* __restrict__ mp = mapP + (size_t)v * plane;
-            const float2 dm = __ldg(mapC + (size_t)v * plane + (size_t)row * vw.W + col);
+            const float4 dm = __ldg(mapC + (size_t)v * plane + (size_t)row * vw.W + col);
             float vis = mh_visible((-cz / 2.0f) * 255.0f, dm.x);
             if (oob) vis = -1.0f;
             float l_w = 0.0f, w = 0.0f;
@@ -72,8 +72,7 @@ refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __re
 #pragma unroll
                     for (int dj = 0; dj < MAXP; ++dj) {
                         if (dj < P) {
-                            float x0, x1;
-                            mh_normalize2(t[dj].x, t[dj].y, x0, x1);
+                            const float x0 = t[dj].x, x1 = t[dj].y;               // stored normalised (pmvo_views.cu)
                             const float cf = fminf(fmaxf(t[dj].z, 1e-6f), 1.0f);
                             const float l = 1.0f - fabsf(x0 * y0 + x1 * y1);
                             if (di == 0 && dj == 0) { bl = l; bc = cf; }

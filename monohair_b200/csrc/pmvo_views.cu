@@ -1,6 +1,9 @@
 // Packing of the per-view maps into the two resident planes the PMVO kernels gather from.
-//   mapC float2 {depth, mask'}          one 8 B texel per centre-pixel query (filter / head / visibility)
-//   mapP float4 {ori_r, ori_c, conf, max_PxP conf}   one 16 B texel per patch entry
+//   mapC float4 {depth, mask', ori_row, ori_col}     one 16 B texel per centre-pixel query (raw orientation: the 2 px
+//                                                    step of sample_next_3d_pos uses it un-normalised, PMVO.py:300)
+//   mapP float4 {unit_row, unit_col, conf, max_PxP conf}   one 16 B texel per patch entry; the direction is stored
+//                already normalised the way torch.cosine_similarity normalises it (x / max(||x||, 1e-8)), so the
+//                patch scans do not repeat a sqrt and two divisions per entry
 // The PxP maximum with edge clamping (get_c_patch + torch.max, PMVO.py:415-418 / :162) equals a max filter
 // over the window intersected with the image, so it is computed once per view here (separable: rows then cols
 // through a shared-memory tile) instead of P*P gathers per (point, view).
@@ -46,7 +49,7 @@ extern "C" int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int3
     MH_CHECK_ARG(depth && ori && conf && mask && mapC_ && mapP_, "null pointer");
     MH_CHECK_ARG(H > 0 && W > 0 && v >= 0, "bad size");
     MH_CHECK_ARG(P >= 1 && (P & 1) && P / 2 <= MAX_HALF, "patch size must be odd and <= 17");
-    float2* mapC = reinterpret_cast<float2*>(mapC_) + (size_t)v * H * W;
+    float4* mapC = reinterpret_cast<float4*>(mapC_) + (size_t)v * H * W;
     float4* mapP = reinterpret_cast<float4*>(mapP_) + (size_t)v * H * W;
     dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
     auto conf_at = [=] __device__(int y, int x) { return __ldg(conf + (size_t)y * W + x); };
@@ -54,9 +57,11 @@ extern "C" int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int3
         size_t i = (size_t)y * W + x;
         float m = __ldg(mask + i * mask_stride);
         m = (m > 0.2f) ? 1.0f : m;                                   // PMVO.py:427 / :124
-        mapC[i] = make_float2(__ldg(depth + i * depth_stride), m);
-        float2 o = __ldg(reinterpret_cast<const float2*>(ori) + i);
-        mapP[i] = make_float4(o.x, o.y, __ldg(conf + i), cmax);
+        const float2 o = __ldg(reinterpret_cast<const float2*>(ori) + i);
+        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, o.x, o.y);
+        float n0, n1;
+        mh_normalize2(o.x, o.y, n0, n1);
+        mapP[i] = make_float4(n0, n1, __ldg(conf + i), cmax);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
     MH_COUNT_LAUNCH();
@@ -73,7 +78,7 @@ extern "C" int mh_views_pack_f64(void* stream, int32_t v, int32_t H, int32_t W, 
     MH_CHECK_ARG(depth && ori && conf && mask && mapC_ && mapP_, "null pointer");
     MH_CHECK_ARG(H > 0 && W > 0 && v >= 0, "bad size");
     MH_CHECK_ARG(P >= 1 && (P & 1) && P / 2 <= MAX_HALF, "patch size must be odd and <= 17");
-    float2* mapC = reinterpret_cast<float2*>(mapC_) + (size_t)v * H * W;
+    float4* mapC = reinterpret_cast<float4*>(mapC_) + (size_t)v * H * W;
     float4* mapP = reinterpret_cast<float4*>(mapP_) + (size_t)v * H * W;
     dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
     auto conf_at = [=] __device__(int y, int x) { return (float)__ldg(conf + (size_t)y * W + x); };
@@ -81,9 +86,12 @@ extern "C" int mh_views_pack_f64(void* stream, int32_t v, int32_t H, int32_t W, 
         size_t i = (size_t)y * W + x;
         float m = (float)__ldg(mask + i * mask_stride);
         m = (m > 0.2f) ? 1.0f : m;
-        mapC[i] = make_float2(__ldg(depth + i * depth_stride), m);
-        const double2 o = __ldg(reinterpret_cast<const double2*>(ori) + i);
-        mapP[i] = make_float4((float)o.x, (float)o.y, (float)__ldg(conf + i), cmax);
+        const double2 od = __ldg(reinterpret_cast<const double2*>(ori) + i);
+        const float ox = (float)od.x, oy = (float)od.y;
+        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, ox, oy);
+        float n0, n1;
+        mh_normalize2(ox, oy, n0, n1);
+        mapP[i] = make_float4(n0, n1, (float)__ldg(conf + i), cmax);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
     MH_COUNT_LAUNCH();
@@ -98,7 +106,7 @@ extern "C" int mh_views_pack_u8(void* stream, int32_t v, int32_t H, int32_t W, i
     MH_CHECK_ARG(depth && ori_gray && conf_u8 && mask_u8 && ori_lut && conf_lut && mask_lut && mapC_ && mapP_, "null pointer");
     MH_CHECK_ARG(H > 0 && W > 0 && v >= 0, "bad size");
     MH_CHECK_ARG(P >= 1 && (P & 1) && P / 2 <= MAX_HALF, "patch size must be odd and <= 17");
-    float2* mapC = reinterpret_cast<float2*>(mapC_) + (size_t)v * H * W;
+    float4* mapC = reinterpret_cast<float4*>(mapC_) + (size_t)v * H * W;
     float4* mapP = reinterpret_cast<float4*>(mapP_) + (size_t)v * H * W;
     dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
     // conf_lut is monotone (k/255) so the max of decoded values is the decode of the max.
@@ -107,9 +115,12 @@ extern "C" int mh_views_pack_u8(void* stream, int32_t v, int32_t H, int32_t W, i
         size_t i = (size_t)y * W + x;
         float m = __ldg(mask_lut + __ldg(mask_u8 + i));               // lut already applies <50 -> 0 and /255
         m = (m > 0.2f) ? 1.0f : m;
-        mapC[i] = make_float2(__ldg(depth + i * depth_stride), m);
-        int g = __ldg(ori_gray + i);
-        mapP[i] = make_float4(__ldg(ori_lut + 2 * g), __ldg(ori_lut + 2 * g + 1), __ldg(conf_lut + __ldg(conf_u8 + i)), cmax);
+        const int g = __ldg(ori_gray + i);
+        const float ox = __ldg(ori_lut + 2 * g), oy = __ldg(ori_lut + 2 * g + 1);
+        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, ox, oy);
+        float n0, n1;
+        mh_normalize2(ox, oy, n0, n1);
+        mapP[i] = make_float4(n0, n1, __ldg(conf_lut + __ldg(conf_u8 + i)), cmax);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
     MH_COUNT_LAUNCH();

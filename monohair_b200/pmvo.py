@@ -59,7 +59,7 @@ class PMVO(nn.Module):
         self.V, self.H, self.W = V, H, W
         dev = self.device
         with torch.cuda.device(dev):
-            self.mapC = torch.empty((V, H, W, 2), dtype=torch.float32, device=dev)
+            self.mapC = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
             self.mapP = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
             self.cam = torch.stack([c.record() for c in self.camera]).to(dev).contiguous()
             st = stream_ptr(dev)
@@ -126,7 +126,7 @@ class PMVO(nn.Module):
         mm[mm < 50] = 0
         mask_lut = torch.from_numpy(mm / 255.).type(torch.float).to(dev)
         with torch.cuda.device(dev):
-            self.mapC = torch.empty((V, H, W, 2), dtype=torch.float32, device=dev)
+            self.mapC = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
             self.mapP = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
             self.cam = torch.stack([c.record() for c in self.camera]).to(dev).contiguous()
             st = stream_ptr(dev)
