@@ -73,6 +73,8 @@ def full(rep, out_md):
     for name, d in res.items():
         out_md.write(f"\n### `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
         for k, (v, u) in d.items():
+            if "nan" in v:
+                continue                      # ncu could not collect this metric for this kernel (replay mismatch)
             out_md.write(f"| {k} | {v} | {u} |\n")
     return res
 
@@ -93,7 +95,7 @@ def main():
         res = full(rep, f)
     tr = {}
     for name, d in res.items():
-        if "dram__bytes_read.sum" in d:
+        if "dram__bytes_read.sum" in d and "nan" not in d["dram__bytes_read.sum"][0]:
             tr[name.split("<")[0]] = {"workload": workload, "points_per_launch": int(ppl), "kernel": name,
                                       "dram_bytes_per_launch": to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])}
     json.dump(tr, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
