@@ -36,6 +36,38 @@ def _f32(a, dev, non_blocking=False):
     return t.to(dev, non_blocking=non_blocking).type(torch.float).contiguous()
 
 
+def _world():
+    """(dist module, rank, world) when torch.distributed is initialised with more than one rank, else (None, 0, 1)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and SHARD_VIEW_UPLOAD:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+SHARD_VIEW_UPLOAD = True   # multi-GPU: each rank uploads + packs only its block of views, planes are all-gathered over NVLink
+
+
+def _alloc_planes(V, H, W, dev):
+    """-> (mapC, mapP, first view of this rank, one-past-last view, finish())."""
+    dist, r, w = _world()
+    if dist is None:
+        mapC = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
+        mapP = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
+        return mapC, mapP, 0, V, 0, (lambda: (mapC, mapP))
+    per = (V + w - 1) // w
+    a, b = min(r * per, V), min((r + 1) * per, V)
+    locC = torch.zeros((per, H, W, 4), dtype=torch.float32, device=dev)
+    locP = torch.zeros((per, H, W, 4), dtype=torch.float32, device=dev)
+
+    def finish():
+        fullC = torch.empty((w * per, H, W, 4), dtype=torch.float32, device=dev)
+        fullP = torch.empty((w * per, H, W, 4), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(fullC, locC)
+        dist.all_gather_into_tensor(fullP, locP)
+        return fullC[:V], fullP[:V]
+    return locC, locP, a, b, a, finish
+
+
 class PMVO(nn.Module):
     """Drop-in for the reference class (PMVO.py:13-37).  The per-view maps are packed once into two resident
     planes per view (see csrc/pmvo_views.cu); everything else runs in fused kernels."""
@@ -59,8 +91,7 @@ class PMVO(nn.Module):
         self.V, self.H, self.W = V, H, W
         dev = self.device
         with torch.cuda.device(dev):
-            self.mapC = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
-            self.mapP = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
+            mapC, mapP, v_lo, v_hi, v_off, finish = _alloc_planes(V, H, W, dev)
             self.cam = torch.stack([c.record() for c in self.camera]).to(dev).contiguous()
             st = stream_ptr(dev)
             stage = {}
@@ -78,6 +109,8 @@ class PMVO(nn.Module):
                 return buf
 
             for v, k in enumerate(self.camera_key):
+                if not (v_lo <= v < v_hi):
+                    continue                                  # another rank uploads this view
                 d_h, o_h, c_h, m_h = depths[k], Ori[k], Conf[k], masks[k]
                 dts = [(x.dtype if torch.is_tensor(x) else torch.from_numpy(np.asarray(x)[:0].copy()).dtype) for x in (d_h, o_h, c_h, m_h)]
                 f64_path = dts[0] == torch.float32 and all(t == torch.float64 for t in dts[1:])
@@ -90,8 +123,9 @@ class PMVO(nn.Module):
                 ds = d.shape[2] if d.dim() == 3 else 1
                 ms = m.shape[2] if m.dim() == 3 else 1
                 fn = lib().mh_views_pack_f64 if f64_path else lib().mh_views_pack
-                check(fn(st, v, H, W, self.patch_size, ptr(d), ds, ptr(o), ptr(c), ptr(m), ms,
-                         ptr(self.mapC), ptr(self.mapP)), "mh_views_pack")
+                check(fn(st, v - v_off, H, W, self.patch_size, ptr(d), ds, ptr(o), ptr(c), ptr(m), ms,
+                         ptr(mapC), ptr(mapP)), "mh_views_pack")
+            self.mapC, self.mapP = finish()
         self._views = MhViews(V, H, W, self.patch_size, self.mapC.data_ptr(), self.mapP.data_ptr(), self.cam.data_ptr())
         self._offsets = self._sample_offsets(90).to(dev)
 
@@ -126,22 +160,24 @@ class PMVO(nn.Module):
         mm[mm < 50] = 0
         mask_lut = torch.from_numpy(mm / 255.).type(torch.float).to(dev)
         with torch.cuda.device(dev):
-            self.mapC = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
-            self.mapP = torch.empty((V, H, W, 4), dtype=torch.float32, device=dev)
+            mapC, mapP, v_lo, v_hi, v_off, finish = _alloc_planes(V, H, W, dev)
             self.cam = torch.stack([c.record() for c in self.camera]).to(dev).contiguous()
             st = stream_ptr(dev)
             as_t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
-            d_all = as_t(depth).to(dev, non_blocking=True)
-            o_all = as_t(ori_gray).to(dev, non_blocking=True)
-            c_all = as_t(conf_u8).to(dev, non_blocking=True)
-            m_all = as_t(mask_u8).to(dev, non_blocking=True)
+            d_all, o_all, c_all, m_all = as_t(depth), as_t(ori_gray), as_t(conf_u8), as_t(mask_u8)
             assert d_all.dtype == torch.float32 and o_all.dtype == torch.uint8 and c_all.dtype == torch.uint8 \
                 and m_all.dtype == torch.uint8
             assert d_all.shape == (V, H, W) and o_all.shape == (V, H, W) and c_all.shape == (V, H, W) and m_all.shape == (V, H, W)
-            for v in range(V):
-                check(lib().mh_views_pack_u8(st, v, H, W, self.patch_size, ptr(d_all[v]), 1, ptr(o_all[v]),
-                                             ptr(c_all[v]), ptr(m_all[v]), ptr(ori_lut), ptr(conf_lut), ptr(mask_lut),
-                                             ptr(self.mapC), ptr(self.mapP)), "mh_views_pack_u8")
+            d_all = d_all[v_lo:v_hi].to(dev, non_blocking=True)
+            o_all = o_all[v_lo:v_hi].to(dev, non_blocking=True)
+            c_all = c_all[v_lo:v_hi].to(dev, non_blocking=True)
+            m_all = m_all[v_lo:v_hi].to(dev, non_blocking=True)
+            for v in range(v_lo, v_hi):
+                j = v - v_lo
+                check(lib().mh_views_pack_u8(st, v - v_off, H, W, self.patch_size, ptr(d_all[j]), 1, ptr(o_all[j]),
+                                             ptr(c_all[j]), ptr(m_all[j]), ptr(ori_lut), ptr(conf_lut), ptr(mask_lut),
+                                             ptr(mapC), ptr(mapP)), "mh_views_pack_u8")
+            self.mapC, self.mapP = finish()
             self._keep = (ori_lut, conf_lut, mask_lut)
         self._views = MhViews(V, H, W, self.patch_size, self.mapC.data_ptr(), self.mapP.data_ptr(), self.cam.data_ptr())
         self._offsets = self._sample_offsets(90).to(dev)

@@ -26,12 +26,25 @@ def main():
     P.scalp_tree, P.scalp_max = scalp, scalp.max(0)
     pm = P.PMVO.from_u8(cameras_from_scene(sc), sc.depth, sc.ori_gray, sc.conf_u8, sc.mask_u8, device=dev,
                         image_size=[sc.H, sc.W], patch_size=7, visible_threshold=1, conf_threshold=0.15)
+    # view-sharded upload (+ all-gather of the packed planes over NCCL) == every rank packing every view
+    P.SHARD_VIEW_UPLOAD = False
+    Ori, Conf = sc.ref_ori_conf()
+    pm_full = P.PMVO(cameras_from_scene(sc), sc.ref_depths(), Ori, Conf, sc.ref_masks(), device=dev,
+                     image_size=[sc.H, sc.W], patch_size=7, visible_threshold=1, conf_threshold=0.15)
+    P.SHARD_VIEW_UPLOAD = True
+    pm_f64 = P.PMVO(cameras_from_scene(sc), sc.ref_depths(), Ori, Conf, sc.ref_masks(), device=dev,
+                    image_size=[sc.H, sc.W], patch_size=7, visible_threshold=1, conf_threshold=0.15)
+    maps_ok = (torch.equal(pm.mapC, pm_full.mapC) and torch.equal(pm.mapP, pm_full.mapP)
+               and torch.equal(pm_f64.mapC, pm_full.mapC) and torch.equal(pm_f64.mapP, pm_full.mapP))
+    if dist.get_rank() == 0:
+        print(f"sharded maps identical: {maps_ok}")
+    del pm_full, pm_f64
     c = torch.from_numpy(cand).to(dev).float()
     multi = pipeline.pmvo_job_device(pm, c, 0.025)
     pipeline._FORCE_SINGLE = True
     single = pipeline.pmvo_job_device(pm, c, 0.025)
     pipeline._FORCE_SINGLE = False
-    ok = True
+    ok = maps_ok
     for k in ("surface", "filter", "select_o", "min_loss", "high_conf", "refine_o", "refine_loss", "fu_ori", "volume"):
         same = torch.equal(multi[k], single[k])
         ok &= same
