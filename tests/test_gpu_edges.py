@@ -1,0 +1,128 @@
+"""GPU edge cases the reference's behaviour defines implicitly: degenerate points (NaN propagation), ragged sizes,
+minimum / odd view counts, other patch sizes, trace termination rules."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _pmvo(V, H, W, P, seed, conf_thr=0.15):
+    from monohair_b200 import synthetic as syn
+    from monohair_b200.camera import cameras_from_scene
+    from monohair_b200.pmvo import PMVO
+    from oracle import pmvo_oracle as O
+    sc = syn.make_scene(V=V, H=H, W=W, seed=seed)
+    Ori, Conf = sc.ref_ori_conf()
+    pm = PMVO(cameras_from_scene(sc), sc.ref_depths(), Ori, Conf, sc.ref_masks(), device="cuda:0", image_size=[H, W],
+              patch_size=P, visible_threshold=1, conf_threshold=conf_thr)
+    return sc, pm, O.ViewMaps.from_scene(sc)
+
+
+@pytest.mark.parametrize("V,H,W,P", [(20, 90, 150, 3), (21, 101, 163, 9), (33, 64, 64, 1), (23, 120, 90, 11)])
+def test_forward_and_filter_vs_oracle_other_shapes(V, H, W, P):
+    from monohair_b200 import synthetic as syn
+    from oracle import pmvo_oracle as O
+    sc, pm, vm = _pmvo(V, H, W, P, seed=V)
+    cand = syn.candidate_points(n_cells=700, num_per_grid=2, seed=V)
+    pts = torch.from_numpy(cand).float()
+    so, fo, cnt_o = O.filter_points(vm, pts, P, 1, 0.15)
+    s, sp, f = pm.filter_points(pts)
+    assert np.array_equal(s.cpu().numpy(), so.numpy()) and np.array_equal(f.cpu().numpy(), fo.numpy())
+    sel = cand[so.numpy()][:40]
+    _, o_o, l_o, hc_o = O.forward(vm, sel, P, 0.15)
+    _, ori, loss, hc = pm.forward(sel)
+    assert np.abs(loss.cpu().numpy() - l_o.numpy()).max() <= 1e-5
+    assert np.mean(np.abs(ori.cpu().numpy() - o_o.numpy()).max(1) <= 1e-4) >= 0.9
+    assert np.array_equal(hc.cpu().numpy(), hc_o.numpy())
+
+
+def test_degenerate_points_nan_semantics_match_oracle():
+    """points no view sees: all weights are 0 -> 0/0 in the reference (PMVO.py:198-201); NaN must propagate the same way."""
+    from oracle import pmvo_oracle as O
+    sc, pm, vm = _pmvo(22, 96, 128, 5, seed=9)
+    far = np.array([[3.0, 3.0, 3.0], [0.0, 0.0, 0.0], [0.0, 5.0, 0.0], [-0.101, 0.0, 0.0]])   # outside / centre of the head
+    _, o_o, l_o, hc_o = O.forward(vm, far, 5, 0.15)
+    _, ori, loss, hc = pm.forward(far)
+    l, lo = loss.cpu().numpy(), l_o.numpy()
+    assert np.array_equal(np.isnan(l), np.isnan(lo))
+    assert np.allclose(l[~np.isnan(lo)], lo[~np.isnan(lo)], atol=1e-5)
+    assert np.array_equal(hc.cpu().numpy(), hc_o.numpy())
+    s, sp, f = pm.filter_points(torch.from_numpy(far).float())
+    so, fo, _ = O.filter_points(vm, torch.from_numpy(far).float(), 5, 1, 0.15)
+    assert np.array_equal(s.cpu().numpy(), so.numpy()) and np.array_equal(f.cpu().numpy(), fo.numpy())
+
+
+def test_forward_requires_twenty_views():
+    from monohair_b200._lib import MonoHairError
+    sc, pm, vm = _pmvo(12, 64, 64, 3, seed=1)
+    with pytest.raises(MonoHairError, match="20 views"):
+        pm.forward(np.zeros((4, 3)))
+
+
+def _solver_from(occ, ori):
+    """occ [Z,Y,X], ori [3,Z,Y,X] in HairGrowing's frame -> solver + oracle volume."""
+    from monohair_b200.hairgrow import HairGrowing
+    from oracle import hairgrow_oracle as Hh
+    vol = torch.zeros(occ.shape + (4,), device="cuda:0")
+    vol[..., :3] = torch.from_numpy(ori).permute(1, 2, 3, 0).cuda()
+    vol[..., 3] = torch.from_numpy(occ).cuda()
+    return HairGrowing(volume=vol, device="cuda:0"), Hh.Volume(occ, ori)
+
+
+def test_trace_termination_rules_vs_oracle():
+    from oracle import hairgrow_oracle as Hh
+    Z, Y, X = 24, 300, 20
+    occ = np.zeros((Z, Y, X), np.float32)
+    ori = np.zeros((3, Z, Y, X), np.float32)
+    occ[10:14, :, 8:12] = 1                       # a long straight column along +y: hits the 256-step cap both ways
+    ori[1, 10:14, :, 8:12] = 1.0
+    ori[0, 10:14, 200:, 8:12] = 0.8               # a kink (dot = 0.78 < 0.85) stops the walk at y = 200
+    ori[1, 10:14, 200:, 8:12] = 0.6
+    occ[2:4, 5:9, 2:4] = 1                        # a blob with zero orientation: never moves, dot = 0 < thr -> < 5 points
+    hg, volc = _solver_from(occ, ori)
+    seeds = np.array([[9.2, 150.3, 11.7], [9.9, 20.1, 12.5], [9.5, 290.0, 10.2], [2.5, 6.5, 2.5], [-3.0, 150.0, 11.0],
+                      [9.0, 400.0, 11.0], [15.0, 150.0, 11.0]], np.float32)
+    pts, off, ln = hg._trace_batch(torch.from_numpy(seeds).cuda(), 0.85)
+    flag = np.zeros_like(occ)
+    for i, sd in enumerate(seeds):
+        row = sd.copy() - 0.5                      # oracle.trace adds 0.5 + jitter*0.5: feed it the un-jittered seed
+        s = Hh.trace(volc, row, flag, 0.85, np.zeros(3, np.float32))
+        n = int(ln[i])
+        if s is None:
+            assert n == 0, (i, n)
+        else:
+            got = pts[int(off[i]):int(off[i]) + n].cpu().numpy()
+            assert got.shape == s.shape and np.array_equal(got, s), i
+    assert int(ln.max()) <= 513 and int(ln[0]) > 200
+
+
+def test_trace_empty_volume_and_scalp_none():
+    occ = np.zeros((8, 8, 8), np.float32)
+    ori = np.zeros((3, 8, 8, 8), np.float32)
+    hg, volc = _solver_from(occ, ori)
+    strands = hg.randomlyGenerateSegments(0.85)
+    assert strands == []
+    roots = torch.tensor([[4.0, 1.0, 4.0]])
+    normals = torch.tensor([[0.0, 1.0, 0.0]])
+    s, num_root = hg.GenerateGuideStrandFromScalp(roots, normals, None, 0.85)
+    assert s == [] and num_root == 0               # 25 inner steps through empty space -> None (HairGrow.py:216-221)
+
+
+@pytest.mark.parametrize("H,W", [(37, 53), (128, 130), (9, 400)])
+def test_gabor_ragged_sizes_vs_oracle(H, W):
+    from monohair_b200.gabor import calOrientationGabor
+    from oracle import gabor_oracle as G
+    rng = np.random.default_rng(H * W)
+    img = (rng.normal(0, 0.05, (H, W))).astype(np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    img += (0.1 * np.cos(2 * np.pi * (xx * math.cos(0.7) + yy * math.sin(0.7)) / 4.3)).astype(np.float32)
+    two_o, orient_o, conf_o, res = G.gabor_orientation(img)
+    two, orient, conf = calOrientationGabor()(torch.from_numpy(img)[None, None].cuda())
+    res = res.numpy()
+    top2 = np.sort(res, axis=0)[-2:]
+    ok = (top2[1] - top2[0]) / res.max() > 1e-4
+    assert np.array_equal(orient[0, 0].cpu().numpy()[ok], orient_o.numpy()[ok])
+    assert np.abs(conf[0, 0].cpu().numpy() - conf_o.numpy())[ok].max() <= 2e-3
