@@ -165,9 +165,9 @@ static int check_vol(const void* volume, int gx, int gy, int gz) {
 
 extern "C" int mh_trace_count(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* seeds,
                               int64_t n, float thr_dot, int32_t max_steps, int32_t* n_fwd, int32_t* n_bwd) {
+    if (n == 0) return 0;
     if (check_vol(volume, gx, gy, gz)) return 1;
     MH_CHECK_ARG(seeds && n_fwd && n_bwd && max_steps > 0, "bad arguments");
-    if (n == 0) return 0;
     Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
     trace_count_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, seeds, n, thr_dot, max_steps, n_fwd, n_bwd);
     MH_COUNT_LAUNCH();
@@ -178,9 +178,9 @@ extern "C" int mh_trace_count(void* stream, const void* volume, int32_t gx, int3
 extern "C" int mh_trace_write(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* seeds,
                               int64_t n, float thr_dot, int32_t max_steps, const int32_t* n_fwd, const int32_t* n_bwd,
                               const int64_t* offsets, int32_t min_len, float* points_out) {
+    if (n == 0) return 0;
     if (check_vol(volume, gx, gy, gz)) return 1;
     MH_CHECK_ARG(seeds && n_fwd && n_bwd && offsets && points_out && max_steps > 0, "bad arguments");
-    if (n == 0) return 0;
     Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
     trace_write_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, seeds, n, thr_dot, max_steps, n_fwd, n_bwd, offsets, min_len, points_out);
     MH_COUNT_LAUNCH();
@@ -191,9 +191,9 @@ extern "C" int mh_trace_write(void* stream, const void* volume, int32_t gx, int3
 extern "C" int mh_trace_from_scalp(void* stream, const void* volume, int32_t gx, int32_t gy, int32_t gz, const float* roots,
                                    const float* normals, int64_t n, float thr_dot, int32_t max_steps, int32_t max_inner,
                                    float* points_out, int32_t* length) {
+    if (n == 0) return 0;
     if (check_vol(volume, gx, gy, gz)) return 1;
     MH_CHECK_ARG(roots && normals && points_out && length && max_steps > 0, "bad arguments");
-    if (n == 0) return 0;
     Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
     trace_scalp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, roots, normals, n, thr_dot, max_steps, max_inner, points_out, length);
     MH_COUNT_LAUNCH();
@@ -204,9 +204,9 @@ extern "C" int mh_trace_from_scalp(void* stream, const void* volume, int32_t gx,
 extern "C" int mh_accept_strands(void* stream, const float* points, const int64_t* offsets, const int32_t* lengths,
                                  const float* seeds, int64_t n, int32_t gx, int32_t gy, int32_t gz, int32_t mode,
                                  float* flag, uint8_t* accepted) {
+    if (n == 0) return 0;
     MH_CHECK_ARG(points && offsets && lengths && flag && accepted && (mode == 1 || seeds), "null pointer");
     MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && (mode == 0 || mode == 1), "bad arguments");
-    if (n == 0) return 0;
     accept_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(points, offsets, lengths, seeds, n, gx, gy, gz, mode, flag, accepted);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
