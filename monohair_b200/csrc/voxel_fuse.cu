@@ -11,6 +11,7 @@
 // its 8 B of bucket bounds and writes its 16 B fully coalesced.
 // Bound: HBM streaming.  Algorithmic bytes = n*(12+12) point reads + 4 B/voxel count write+read (x2 for the
 // scan) + 16 B/voxel volume write; 256x256x192: 12.58 M voxels -> 201 MB of volume writes dominate.
+#include <algorithm>
 #include "mh_common.cuh"
 #include "mh_torch_sum.cuh"
 
@@ -42,28 +43,50 @@ __global__ void __launch_bounds__(256)
 count_kernel_vf(VGrid g, const float* __restrict__ pts, int64_t n, int* __restrict__ cnt, int* __restrict__ key,
                 int* __restrict__ rank, int* __restrict__ occ_list, int* __restrict__ hdr, int* __restrict__ vox_index) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int x, y, z;
-    p2v(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], x, y, z);
-    const int k = (z * g.gy + y) * g.gx + x;
-    key[i] = k;
-    if (vox_index) vox_index[i] = (x * g.gy + y) * g.gz + z;
-    const int r = atomicAdd(cnt + k, 1);
-    rank[i] = r;
-    if (r == 0) occ_list[atomicAdd(hdr, 1)] = k;
+    const int lane = threadIdx.x & 31;
+    int k = -1 - lane;                                   // inactive lanes get distinct dummy keys
+    if (i < n) {
+        int x, y, z;
+        p2v(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], x, y, z);
+        k = (z * g.gy + y) * g.gx + x;
+        key[i] = k;
+        if (vox_index) vox_index[i] = (x * g.gy + y) * g.gz + z;
+    }
+    // warp-aggregated arrival ranks: neighbouring points usually share a voxel, so one atomic serves the group
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader && i < n) base = atomicAdd(cnt + k, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) {
+        const int r = base + __popc(peers & ((1u << lane) - 1));
+        rank[i] = r;
+        if (r == 0) occ_list[atomicAdd(hdr, 1)] = k;
+    }
 }
 
-// Pass 2 (per occupied voxel): reserve a bucket [base, base+count) (any disjoint placement will do, so a plain atomic
-// cursor replaces a scan); the dense plane now holds the bucket base.
+// Pass 2 (per occupied voxel): reserve a bucket [base, base+count) (any disjoint placement will do, so an atomic
+// cursor -- one add per warp -- replaces a scan); the dense plane now holds the bucket base.
 __global__ void __launch_bounds__(256)
 bucket_kernel(const int* __restrict__ occ_list, int* __restrict__ cnt, int* __restrict__ cnt_list, int* __restrict__ hdr) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= hdr[0]) return;
-    const int k = occ_list[j];
-    const int c = cnt[k];
-    cnt_list[j] = c;
-    cnt[k] = atomicAdd(hdr + 2, c);
-    atomicMax(hdr + 1, c);
+    const int M = hdr[0];
+    const int lane = threadIdx.x & 31;
+    for (int j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; j0 < M; j0 += gridDim.x * blockDim.x) {
+        const int j = j0 + lane;
+        int c = 0, k = 0;
+        if (j < M) { k = occ_list[j]; c = cnt[k]; cnt_list[j] = c; }
+        int incl = c, mx = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        int base = 0;
+        if (lane == 31) { base = atomicAdd(hdr + 2, incl); atomicMax(hdr + 1, mx); }
+        base = __shfl_sync(0xffffffffu, base, 31);
+        if (j < M) cnt[k] = base + incl - c;
+    }
 }
 
 // Pass 3 (per point): drop the point id into its voxel's bucket.
@@ -290,7 +313,7 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
         const unsigned nb = (unsigned)((n + 255) / 256);
         count_kernel_vf<<<nb, 256, 0, st>>>(g, points, n, cnt, key, rank, occ_list, hdr, vox_index);
         MH_COUNT_LAUNCH();
-        bucket_kernel<<<nb, 256, 0, st>>>(occ_list, cnt, cnt_list, hdr);
+        bucket_kernel<<<(unsigned)std::min<int64_t>(nb, (int64_t)mh_sm_count() * 8), 256, 0, st>>>(occ_list, cnt, cnt_list, hdr);
         MH_COUNT_LAUNCH();
         scatter_kernel<<<nb, 256, 0, st>>>(n, key, rank, cnt, bucket);
         MH_COUNT_LAUNCH();
