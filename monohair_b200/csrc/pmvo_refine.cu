@@ -350,39 +350,77 @@ knn_query_fast_kernel(Grid g, const float* __restrict__ ref, const int* __restri
         double U = INF;
         bool fail = false, done = false;
         for (int R = 0; R <= maxR && !fail && !done; ++R) {
-            const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
-            const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
-            const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
-            for (int z = z0; z <= z1 && !fail; ++z)
-                for (int y = y0; y <= y1 && !fail; ++y) {
-                    const bool edge_zy = (abs(z - cz) == R) || (abs(y - cy) == R);
-                    for (int seg = 0; seg < (edge_zy ? 1 : 2) && !fail; ++seg) {
-                        int xa, xb;
-                        if (edge_zy) { xa = x0; xb = x1; }
+            // The shell of radius R as a flat list of item ranges: every (z,y) row gets two slots -- an edge row
+            // (|dz| == R or |dy| == R) is one contiguous x-range, an interior row contributes its two end cells.
+            // Lanes fetch the ranges of 32 slots at once, a warp scan lays them out, and the candidates are then
+            // gathered four per lane per round, so the dependent loads (range -> item -> coordinates) are paid per
+            // batch of 128 candidates instead of per row.
+            const int side = 2 * R + 1, nslots = 2 * side * side;
+            for (int slot0 = 0; slot0 < nslots && !fail; slot0 += 32) {
+                const int slot = slot0 + lane;
+                int s_beg = 0, s_len = 0;
+                if (slot < nslots) {
+                    const int row = slot >> 1, half2 = slot & 1;
+                    const int z = cz - R + row / side, y = cy - R + row % side;
+                    if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
+                        const bool edge_zy = (abs(z - cz) == R) || (abs(y - cy) == R);
+                        int xa = 0, xb = -1;
+                        if (edge_zy) { if (half2 == 0) { xa = max(cx - R, 0); xb = min(cx + R, g.nx - 1); } }
                         else {
-                            const int xx = seg == 0 ? cx - R : cx + R;
-                            if (xx < 0 || xx >= g.nx || (seg == 1 && R == 0)) continue;
-                            xa = xb = xx;
+                            const int xx = half2 == 0 ? cx - R : cx + R;
+                            if (xx >= 0 && xx < g.nx && !(half2 == 1 && R == 0)) xa = xb = xx;
                         }
-                        const int rowc = (z * g.ny + y) * g.nx;
-                        const int s = starts[rowc + xa], e = starts[rowc + xb + 1];
-                        for (int it0 = s; it0 < e; it0 += 32) {
-                            const int it = it0 + lane;
-                            bool ok = false;
-                            double d = INF; int ri = 0;
-                            if (it < e) {
-                                ri = items[it];
-                                const double dx = qx - (double)ref[3 * ri], dy = qy - (double)ref[3 * ri + 1], dz = qz - (double)ref[3 * ri + 2];
-                                d = dx * dx + dy * dy + dz * dz;
-                                ok = d <= U;
-                            }
-                            const unsigned m = __ballot_sync(0xffffffffu, ok);
-                            if (nc + __popc(m) > KF_CAP) { fail = true; break; }
-                            if (ok) { const int slot = nc + __popc(m & ((1u << lane) - 1)); sd[slot] = d; si[slot] = ri; }
-                            nc += __popc(m);
+                        if (xb >= xa) {
+                            const int rowc = (z * g.ny + y) * g.nx;
+                            s_beg = starts[rowc + xa];
+                            s_len = starts[rowc + xb + 1] - s_beg;
                         }
                     }
                 }
+                int incl = s_len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - s_len;
+                for (int c0 = 0; c0 < total && !fail; c0 += 128) {
+                    double d4[4]; int r4[4]; bool ok4[4];
+                    int it4[4];
+#pragma unroll
+                    for (int u2 = 0; u2 < 4; ++u2) {
+                        const int c = c0 + lane + 32 * u2;
+                        // segment of candidate c: the last slot whose exclusive offset is <= c (5-step search via shuffles)
+                        int lo = 0;
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1) {
+                            const int probe = lo + step;
+                            const int pe = __shfl_sync(0xffffffffu, excl, probe & 31);
+                            if (probe < 32 && pe <= c) lo = probe;
+                        }
+                        // skip empty slots that share the same offset: take the slot whose range really contains c
+                        const int sb = __shfl_sync(0xffffffffu, s_beg, lo), se = __shfl_sync(0xffffffffu, excl, lo);
+                        it4[u2] = (c < total) ? sb + (c - se) : -1;
+                    }
+#pragma unroll
+                    for (int u2 = 0; u2 < 4; ++u2) r4[u2] = it4[u2] >= 0 ? items[it4[u2]] : -1;
+#pragma unroll
+                    for (int u2 = 0; u2 < 4; ++u2) {
+                        d4[u2] = INF; ok4[u2] = false;
+                        if (r4[u2] >= 0) {
+                            const int ri = r4[u2];
+                            const double dx = qx - (double)ref[3 * ri], dy = qy - (double)ref[3 * ri + 1], dz = qz - (double)ref[3 * ri + 2];
+                            d4[u2] = dx * dx + dy * dy + dz * dz;
+                            ok4[u2] = d4[u2] <= U;
+                        }
+                    }
+#pragma unroll
+                    for (int u2 = 0; u2 < 4; ++u2) {
+                        const unsigned m = __ballot_sync(0xffffffffu, ok4[u2]);
+                        if (nc + __popc(m) > KF_CAP) { fail = true; break; }
+                        if (ok4[u2]) { const int sl = nc + __popc(m & ((1u << lane) - 1)); sd[sl] = d4[u2]; si[sl] = r4[u2]; }
+                        nc += __popc(m);
+                    }
+                }
+            }
             if (fail) break;
             if ((R == 0 && maxR > 0) || nc < K) continue;
             __syncwarp();
