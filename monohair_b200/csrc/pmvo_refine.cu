@@ -320,11 +320,11 @@ knn_query_kernel(Grid g, const float* __restrict__ ref, const int* __restrict__ 
 // ---- fast path: gather ring candidates once, pick a radius by bisection, sort <= 256 survivors once ----------
 // The cell size is ~ the k-NN radius, so rings 0..1 usually hold all k neighbours.  Candidates (squared float64
 // distance, index) of the visited rings are kept in shared memory (KF_CAP per warp).  A bisection on the squared
-// radius finds U >= d_k with at most 256 candidates inside; survivors are compacted, and the search ends when the
+// radius finds U >= d_k with at most KF_SORT candidates inside; survivors are compacted, and the search ends when the
 // visited block contains the ball of radius sqrt(U).  One bitonic sort orders the survivors by (distance, index).
 // Queries that overflow the buffer or cannot be separated (hundreds of equidistant points) are flagged and redone
 // by the general kernel above.
-constexpr int KF_WARPS = 4, KF_CAP = 768, KF_SORT = 256;
+constexpr int KF_WARPS = 4, KF_CAP = 768, KF_SORT = 128;   // survivors sorted once (128: one 28-stage bitonic network)
 
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
