@@ -135,10 +135,13 @@ int mh_refine_update(void* stream, const float* center, const float* upd_loss, c
                      int64_t n, float* ori /*in/out [n][3]*/, float* loss /*out [n]*/);
 
 /* The whole chunk-sequential pass of PMVO.refine step (i) (PMVO.py:608-641): for each chunk of sub_num points, in
- * order: mh_medoid_gather on the CURRENT ori -> mh_pmvo_refine_loss -> mh_refine_update in place. */
+ * order: centre = medoid of the neighbours' CURRENT orientations, loss = re-score of (point, centre), ori <- centre
+ * where |cos| < 0.95 -- later chunks see earlier chunks' updates (Gauss-Seidel across chunks).  Runs as one
+ * persistent dependency-ordered sweep kernel + one re-score launch over all points (see pmvo_refine.cu). */
+int64_t mh_refine_chunks_workspace_bytes(int64_t n, int64_t sub_num);
 int mh_refine_chunks(void* stream, const mh_views* views, const float* points, const int32_t* nbr, int32_t K,
                      const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
-                     float* ori /*in/out*/, float* loss /*out*/, float* scratch /*[sub_num][4] floats*/);
+                     float* ori /*in/out*/, float* loss /*out*/, void* scratch, int64_t scratch_bytes);
 
 /* ---- voxel fusion (PMVO.py:695-726, PMVO_utils.p2v :386-404) ------------------------------------------ */
 int64_t mh_voxel_fuse_workspace_bytes(int64_t n_points, int32_t gx, int32_t gy, int32_t gz);

@@ -44,7 +44,8 @@ _SIGS = {
     "mh_head_count": (C.c_int, [p, VP, p, i64, f32, p]),
     "mh_head_decide": (C.c_int, [p, p, p, p, i64, f64, f64, p]),
     "mh_centre_gather": (C.c_int, [p, VP, p, i64, p, p, p, p, p]),
-    "mh_refine_chunks": (C.c_int, [p, VP, p, p, i32, p, i64, i64, f32, p, p, p]),
+    "mh_refine_chunks": (C.c_int, [p, VP, p, p, i32, p, i64, i64, f32, p, p, p, i64]),
+    "mh_refine_chunks_workspace_bytes": (i64, [i64, i64]),
     "mh_refine_update": (C.c_int, [p, p, p, p, i64, p, p]),
     "mh_pmvo_optimize_workspace_bytes": (i64, [VP, i64]),
     "mh_pmvo_optimize": (C.c_int, [p, VP, p, i64, p, i32, f32, p, p, p, p, p, p, p, p, p, i64]),

@@ -117,10 +117,11 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
         return o, l
     nbr = knn_stage(pts, pts, k, dev)
     filt = head_filter_stage(pm, pts, pm.visible_threshold).to(torch.uint8).contiguous()
-    scratch = torch.empty((sub_num, 4), dtype=torch.float32, device=dev)
+    wsb = lib().mh_refine_chunks_workspace_bytes(n, sub_num)
+    scratch = torch.empty((wsb,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib().mh_refine_chunks(stream_ptr(dev), pm._vp(), ptr(pts), ptr(nbr), k, ptr(filt), n, sub_num,
-                                     float(pm.conf_threshold), ptr(o), ptr(l), ptr(scratch)), "mh_refine_chunks")
+                                     float(pm.conf_threshold), ptr(o), ptr(l), ptr(scratch), wsb), "mh_refine_chunks")
     return o, l
 
 
