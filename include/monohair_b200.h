@@ -144,14 +144,23 @@ int mh_refine_chunks(void* stream, const mh_views* views, const float* points, c
                      float* ori /*in/out*/, float* loss /*out*/, void* scratch, int64_t scratch_bytes);
 
 /* ---- voxel fusion (PMVO.py:695-726, PMVO_utils.p2v :386-404) ------------------------------------------ */
+/* Two buffers: a per-call workspace, and a persistent `plane` (8 B per voxel) that must be all-zero on entry and
+ * is left all-zero on exit (mh_voxel_fuse_plane_init zeroes a fresh one; re-initialise it after a failed call). */
 int64_t mh_voxel_fuse_workspace_bytes(int64_t n_points, int32_t gx, int32_t gy, int32_t gz);
+int64_t mh_voxel_fuse_plane_bytes(int32_t gx, int32_t gy, int32_t gz);
+int mh_voxel_fuse_plane_init(void* stream, void* plane, int32_t gx, int32_t gy, int32_t gz);
 /* points float32 [n][3] (world), dirs float32 [n][3].  Flips dirs to dir.y<=0 (PMVO.py:702-703), voxelises with
  * float64 index math (np.round half-even), takes the per-voxel medoid in original point order and writes the
  * fused volume as float4 [gz][gy][gx] = {ori.x, -ori.y, -ori.z, occ}: the layout/sign HairGrowing.__init__
- * builds from the .mat pair (HairGrow.py:45-55).  vox_index int32 [n] (linear id x*gy*gz+y*gz+z; may be NULL). */
-int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
+ * builds from the .mat pair (HairGrow.py:45-55).  vox_index int32 [n] (linear id x*gy*gz+y*gz+z; may be NULL).
+ * valid (optional): points with valid[i] == 0 are skipped, as if they had been removed from the arrays. */
+int mh_voxel_fuse(void* stream, const float* points, const float* dirs, const uint8_t* valid /*[n] or NULL*/, int64_t n,
                   const double* voxel_min_host /*[3]*/, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
-                  void* volume /*float4 [gz][gy][gx]*/, int32_t* vox_index, void* workspace, int64_t workspace_bytes);
+                  void* volume /*float4 [gz][gy][gx]*/, int32_t* vox_index, void* plane, void* workspace,
+                  int64_t workspace_bytes);
+/* Tuning hook for the volume's zero fill: -1 (default) = memset on an auxiliary stream concurrent with the binning and
+ * medoid kernels; 0..100 = streamed by those kernels' own threads, that percentage by the binning kernel. */
+int mh_voxel_fuse_tune(int32_t fill_bin_pct);
 /* Synchronous: largest per-voxel point count seen by the last mh_voxel_fuse on this workspace (informational). */
 int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host);
 /* Overwrite voxels with given orientations, last writer wins (raw.npy merge, PMVO.py:747-749). */

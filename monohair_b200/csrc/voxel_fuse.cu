@@ -37,156 +37,327 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, 
     if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
 }
 
-// Pass 1 (per point): voxel key, arrival rank inside the voxel (atomic count in a dense int32 plane), and the first
-// arrival of each voxel registers it in the compact list of occupied voxels.
-__global__ void __launch_bounds__(256)
-count_kernel_vf(VGrid g, const float* __restrict__ pts, int64_t n, int* __restrict__ cnt, int* __restrict__ key,
-                int* __restrict__ rank, int* __restrict__ occ_list, int* __restrict__ hdr, int* __restrict__ vox_index) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    int k = -1 - lane;                                   // inactive lanes get distinct dummy keys
-    if (i < n) {
-        int x, y, z;
-        p2v(g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], x, y, z);
-        k = (z * g.gy + y) * g.gx + x;
-        key[i] = k;
-        if (vox_index) vox_index[i] = (x * g.gy + y) * g.gz + z;
+// ---- fusion passes ---------------------------------------------------------------------------------------
+// Shape of the problem: n points (1.7 M) fall into M occupied voxels (81 k, ~20 points each) of a 12.6 M-voxel grid
+// whose 16 B/voxel zero fill (201 MB) is the only bandwidth-sized term; grouping points by voxel is latency bound
+// (atomics, dependent accesses) and the medoid is instruction bound.  The zero fill is therefore streamed by the threads
+// of the two working kernels (fire-and-forget stores that keep HBM busy while the real work waits on latency / issue):
+//   K1 bin     per point : p2v key -> ONE 64-bit atomic on the dense `plane` {count | slot+1} gives the arrival rank;
+//                          the voxel's first arrival allocates the voxel's record from its BLOCK's slot range (shared-
+//                          memory counter: no global allocation counter) and publishes the slot in the high word.  The
+//                          point's {unit direction, id} goes into the record: one contiguous run of (1 + CAP) float4 =
+//                          header {key} + CAP entries; arrivals beyond CAP are pushed on a per-voxel chain.  Then the
+//                          thread streams its share of the fill.
+//   K2 medoid  per voxel : one warp per record, lane = candidate; entries rank-sorted back into point order through
+//                          shared memory; medoid under |cos| in torch.mean's summation order; writes the winner
+//                          {point id, voxel key}; resets the voxel's plane entry; streams the rest of the fill.
+//   K3 apply   per record: winner's raw direction -> the (by now completely zeroed) volume.
+// The plane is persistent workspace state: all-zero on entry, all-zero again on exit (only M entries are touched), so
+// no per-call clear of a dense array and no per-point key/rank arrays exist.  HBM traffic ~= points + directions +
+// volume (+ records, mostly L2-resident between the kernels).
+struct FuseHdr { int n_big, max_cnt, n_over, scratch_cursor, pad[12]; };
+static_assert(sizeof(FuseHdr) == 64, "header size");
+typedef unsigned long long u64;
+constexpr int FUSE_CAP = 32;                 // entries per record
+constexpr int64_t FUSE_STRIDE = FUSE_CAP + 1;
+constexpr int FUSE_BLOCK = 256;              // points per K1 block = record slots owned by the block
+
+__device__ __forceinline__ void fill_zero(float4* __restrict__ vol, int64_t beg, int64_t end) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    int64_t g = beg + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + 3 * stride < end; g += 4 * stride) {
+        __stcs(vol + g, z); __stcs(vol + g + stride, z); __stcs(vol + g + 2 * stride, z); __stcs(vol + g + 3 * stride, z);
     }
-    // warp-aggregated arrival ranks: neighbouring points usually share a voxel, so one atomic serves the group
-    const unsigned peers = __match_any_sync(0xffffffffu, k);
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader && i < n) base = atomicAdd(cnt + k, __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (i < n) {
-        const int r = base + __popc(peers & ((1u << lane) - 1));
-        rank[i] = r;
-        if (r == 0) occ_list[atomicAdd(hdr, 1)] = k;
-    }
+    for (; g < end; g += stride) __stcs(vol + g, z);
 }
 
-// Pass 2 (per occupied voxel): reserve a bucket [base, base+count) (any disjoint placement will do, so an atomic
-// cursor -- one add per warp -- replaces a scan); the dense plane now holds the bucket base.
-__global__ void __launch_bounds__(256)
-bucket_kernel(const int* __restrict__ occ_list, int* __restrict__ cnt, int* __restrict__ cnt_list, int* __restrict__ hdr) {
-    const int M = hdr[0];
-    const int lane = threadIdx.x & 31;
-    for (int j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; j0 < M; j0 += gridDim.x * blockDim.x) {
-        const int j = j0 + lane;
-        int c = 0, k = 0;
-        if (j < M) { k = occ_list[j]; c = cnt[k]; cnt_list[j] = c; }
-        int incl = c, mx = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+// torch.argmax semantics: NaN counts as the maximum, ties go to the lowest index
+__device__ __forceinline__ bool arg_better_max(float s, int k, float best, int bk) {
+    const bool sn = s != s, bn = best != best;
+    if (sn || bn) return sn && (!bn || k < bk);
+    return s > best || (s == best && k < bk);
+}
+
+// spin read of a plane word: relaxed is enough (nothing else is read on the strength of it in this kernel; an acquire
+// would also invalidate L1 on every poll)
+__device__ __forceinline__ u64 vf_ld_relaxed(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one coordinate of p2v: rint(d / vs) with d = p - min.  d * (1/vs) differs from the correctly rounded quotient by a
+// couple of ulps, so both round to the same integer unless the product sits within 1e-9 of a half-integer; only then is
+// the division evaluated.
+__device__ __forceinline__ double p2v_coord(double d, double vs, double inv) {
+    const double q = d * inv;
+    const double f = q - floor(q);
+    if (fabs(f - 0.5) < 1e-9 || !(fabs(q) < 1e9)) return rint(d / vs);
+    return rint(q);
+}
+__device__ __forceinline__ void p2v_fast(const VGrid& g, double inv, float px, float py, float pz, int& x, int& y, int& z) {
+    const double fx = p2v_coord((double)px - g.mx, g.vs, inv);
+    const double fy = p2v_coord(-(double)py - g.my, g.vs, inv);
+    const double fz = p2v_coord(-(double)pz - g.mz, g.vs, inv);
+    x = (int)fmin(fmax(fx, 0.0), (double)(g.gx - 1));
+    y = (int)fmin(fmax(fy, 0.0), (double)(g.gy - 1));
+    z = (int)fmin(fmax(fz, 0.0), (double)(g.gz - 1));
+}
+
+__global__ void __launch_bounds__(FUSE_BLOCK, 8)
+bin_kernel(VGrid g, double inv_vs, const float* __restrict__ pts, const float* __restrict__ dirs,
+           const uint8_t* __restrict__ valid, int64_t n, u64* plane,
+           float4* records, int* over_head, float4* __restrict__ over_ent, int* __restrict__ over_next,
+           int* block_cnt, FuseHdr* hdr, int* __restrict__ vox_index, float4* __restrict__ vol, int64_t fill_end) {
+    __shared__ int s_alloc;
+    const int64_t i = (int64_t)blockIdx.x * FUSE_BLOCK + threadIdx.x;
+    if ((int64_t)blockIdx.x * FUSE_BLOCK < n) {
+        if (threadIdx.x == 0) s_alloc = 0;
+        __syncthreads();
+        const int lane = threadIdx.x & 31;
+        const unsigned lt = (1u << lane) - 1u;
+        const bool active = i < n && (valid == nullptr || valid[i] != 0);
+        int k = -1 - lane;                               // inactive lanes get distinct dummy keys
+        float4 e = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (active) {
+            // both gathers in flight before any arithmetic
+            const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+            float a = dirs[3 * i], b = dirs[3 * i + 1], c = dirs[3 * i + 2];
+            asm volatile("" : "+f"(a), "+f"(b), "+f"(c));              // keep the loads above the p2v branches
+            int x, y, z;
+            p2v_fast(g, inv_vs, px, py, pz, x, y, z);
+            k = (z * g.gy + y) * g.gx + x;
+            if (vox_index) vox_index[i] = (x * g.gy + y) * g.gz + z;
+            if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }   // PMVO.py:702-703
+            const float na = fmaxf(mh_norm3(a, b, c), 1e-8f);        // cosine_similarity's per-operand normalisation
+            e = make_float4(a / na, b / na, c / na, __int_as_float((int)i));
         }
+        // one leader per distinct key in the warp (neighbouring points usually share a voxel)
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(peers) - 1, npeers = __popc(peers);
+        const bool lead = active && lane == leader;
+        int64_t slot1 = 0;
         int base = 0;
-        if (lane == 31) { base = atomicAdd(hdr + 2, incl); atomicMax(hdr + 1, mx); }
-        base = __shfl_sync(0xffffffffu, base, 31);
-        if (j < M) cnt[k] = base + incl - c;
+        bool alloc = false;
+        if (lead) {
+            const u64 old = atomicAdd(plane + k, (u64)npeers);
+            base = (int)(old & 0xffffffffu);
+            slot1 = (int64_t)(old >> 32);
+            alloc = (base == 0);                         // the voxel's first arrival
+        }
+        // first arrivals take a record from the block's slot range and publish slot+1 in the plane's high word
+        const unsigned am = __ballot_sync(0xffffffffu, alloc);
+        if (am) {
+            const int fa = __ffs(am) - 1;
+            int s0 = 0;
+            if (lane == fa) { s0 = atomicAdd(&s_alloc, __popc(am)); atomicAdd(block_cnt + blockIdx.x, __popc(am)); }
+            s0 = __shfl_sync(0xffffffffu, s0, fa);
+            if (alloc) {
+                slot1 = (int64_t)blockIdx.x * FUSE_BLOCK + s0 + __popc(am & lt) + 1;
+                reinterpret_cast<int*>(records + (slot1 - 1) * FUSE_STRIDE)[0] = k;      // read by K2 only
+                atomicAdd(plane + k, (u64)slot1 << 32);
+            }
+        }
+        __syncwarp();
+        if (lead && slot1 == 0) {                        // the allocating warp publishes without waiting on anyone
+            do { slot1 = (int64_t)(vf_ld_relaxed(plane + k) >> 32); } while (slot1 == 0);
+        }
+        slot1 = __shfl_sync(0xffffffffu, slot1, leader);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (active) {
+            const int r = base + __popc(peers & lt);
+            if (r < FUSE_CAP) {
+                records[(slot1 - 1) * FUSE_STRIDE + 1 + r] = e;
+            } else {                                     // crowded voxel: push on its overflow chain
+                const int o = atomicAdd(&hdr->n_over, 1);
+                over_ent[o] = e;
+                over_next[o] = atomicExch(over_head + (slot1 - 1), o + 1);
+            }
+        }
+    }
+    fill_zero(vol, 0, fill_end);                         // after the ordered part: nothing waits on these stores
+}
+
+// |cos| of two unit vectors as torch.cosine_similarity's dot evaluates it
+__device__ __forceinline__ float vf_absdot(const float4& w, const float4& v) { return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); }
+
+// compute_points_similarity (PMVO_utils.py:366-382): argmax_k mean_j |cos(o_k, o_j)| with the points in original order
+// (first-index tie-break).  One warp per record, lane k = candidate k; the row sum follows torch.mean over K contiguous
+// floats (mh_torch_sum.cuh): 8 vector-lane accumulators acc[t & 7] over t < 8*(K/8) (for K < 40 the 4 row accumulators
+// collapse to this sequential form), the scalar tail summed first, then the 8 accumulators added in order; K < 8 takes
+// torch's scalar path.  Records of more than CAP points go through global scratch with the generic summation.
+constexpr int MEDOID_WARPS = 8, MEDOID_SPLIT = 16;        // warps per block; warps sharing one K1 block's records
+
+// warp arg-max of non-negative (or NaN) means with torch.argmax semantics: positive floats and NaN order like their bit
+// patterns (NaN above everything = counts as the maximum), ties go to the lowest candidate index.
+__device__ __forceinline__ int vf_warp_argmax(float mean, int k, bool valid) {
+    const unsigned bits = valid ? (__float_as_uint(mean) & 0x7fffffffu) + 1u : 0u;      // -0 -> +0; 0 = "no candidate"
+    const unsigned mx = __reduce_max_sync(0xffffffffu, bits);
+    return (int)__reduce_min_sync(0xffffffffu, (bits == mx && valid) ? (unsigned)k : 0x7fffffffu);
+}
+
+__global__ void __launch_bounds__(MEDOID_WARPS * 32, 6)
+fuse_medoid_kernel(int64_t n_blocks, const int* __restrict__ block_cnt, const float4* __restrict__ records,
+                   FuseHdr* hdr, int2* __restrict__ big_list, u64* __restrict__ plane, int2* __restrict__ winners,
+                   float4* __restrict__ vol, int64_t fill_beg, int64_t fill_end) {
+    __shared__ float4 s_u[MEDOID_WARPS][FUSE_CAP];
+    __shared__ int4 s_ids[MEDOID_WARPS][FUSE_CAP / 4];
+    fill_zero(vol, fill_beg, fill_end);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* u = s_u[warp];
+    const int4* ids4 = s_ids[warp];
+    int wmax = 0;
+    const int64_t n_items = n_blocks * MEDOID_SPLIT;
+    for (int64_t w = (int64_t)blockIdx.x * MEDOID_WARPS + warp; w < n_items; w += (int64_t)gridDim.x * MEDOID_WARPS) {
+        const int64_t b = w / MEDOID_SPLIT;
+        const int cnt = block_cnt[b];
+        const int r0 = (int)(w % MEDOID_SPLIT);
+        const int mine = (cnt - r0 + MEDOID_SPLIT - 1) / MEDOID_SPLIT;   // this warp's records: r0, r0+SPLIT, ...
+        const float4* rec0 = records + (b * FUSE_BLOCK + r0) * FUSE_STRIDE;
+        for (int c0 = 0; c0 < mine; c0 += 32) {
+            // batch: lane i fetches {key, count} of record c0+i (the two dependent loads of every record, all in flight
+            // together), the record loop below broadcasts them
+            int my_key = 0, my_K = 0;
+            if (c0 + lane < mine) {
+                my_key = reinterpret_cast<const int*>(rec0 + (int64_t)(c0 + lane) * MEDOID_SPLIT * FUSE_STRIDE)[0];
+                my_K = (int)(__ldcg(plane + my_key) & 0xffffffffu);
+            }
+            const int nrec = min(32, mine - c0);
+            float4 e_next = rec0[(int64_t)c0 * MEDOID_SPLIT * FUSE_STRIDE + 1 + lane];
+            for (int c = 0; c < nrec; ++c) {
+                const int64_t ri = (int64_t)(c0 + c) * MEDOID_SPLIT;
+                const float4* rec = rec0 + ri * FUSE_STRIDE;
+                const int64_t slot = b * FUSE_BLOCK + r0 + ri;
+                const float4 e = e_next;
+                if (c + 1 < nrec) e_next = rec[MEDOID_SPLIT * FUSE_STRIDE + 1 + lane];       // next record's entries
+                const int key = __shfl_sync(0xffffffffu, my_key, c);
+                const int K = __shfl_sync(0xffffffffu, my_K, c);
+                wmax = max(wmax, K);
+                int best_id;
+                if (K <= FUSE_CAP) {
+                    const int id = (lane < K) ? __float_as_int(e.w) : 0x7fffffff;
+                    reinterpret_cast<int*>(s_ids[warp])[lane] = id;
+                    __syncwarp();
+                    int rk = 0;                                         // rank = number of smaller ids in the record
+                    for (int t4 = 0; 4 * t4 < K; ++t4) {
+                        const int4 v = ids4[t4];
+                        rk += (v.x < id) + (v.y < id) + (v.z < id) + (v.w < id);
+                    }
+                    if (lane < K) u[rk] = e;
+                    __syncwarp();
+                    const float4 me = u[min(lane, K - 1)];              // candidate = sorted position `lane`
+                    float total;
+                    if (K < 8) {
+                        // torch's scalar path: 4 accumulators over rows of 4, leftovers into the first, then p0+p1+p2+p3
+                        float x[7];
+#pragma unroll
+                        for (int t = 0; t < 7; ++t) x[t] = (t < K) ? vf_absdot(me, u[t]) : 0.0f;
+                        if (K >= 4) {
+                            float p0 = 0.0f + x[0];
+                            const float p1 = 0.0f + x[1], p2 = 0.0f + x[2], p3 = 0.0f + x[3];
+#pragma unroll
+                            for (int t = 4; t < 7; ++t) if (t < K) p0 += x[t];
+                            p0 += p1; p0 += p2; p0 += p3;
+                            total = p0;
+                        } else {
+                            total = 0.0f;
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) if (t < K) total += x[t];
+                        }
+                    } else {
+                        const int nv8 = K & ~7;
+                        float acc[8];
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
+                        for (int t0 = 0; t0 < nv8; t0 += 8) {
+#pragma unroll
+                            for (int l = 0; l < 8; ++l) acc[l] += vf_absdot(me, u[t0 + l]);
+                        }
+                        total = 0.0f;
+                        for (int t = nv8; t < K; ++t) total += vf_absdot(me, u[t]);
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) total += acc[l];
+                    }
+                    const int bk = vf_warp_argmax(total / (float)K, lane, lane < K);
+                    best_id = __float_as_int(u[bk].w);
+                    __syncwarp();
+                } else {
+                    // crowded voxel: left to fuse_medoid_big_kernel (keeps this kernel's register count low)
+                    if (lane == 0) {
+                        big_list[atomicAdd(&hdr->n_big, 1)] = make_int2((int)slot, K);
+                        plane[key] = 0ull;
+                        winners[slot] = make_int2(0, key);
+                    }
+                    continue;
+                }
+                if (lane == 0) {
+                    winners[slot] = make_int2(best_id, key);
+                    plane[key] = 0ull;                   // leave the plane clean for the next call
+                }
+            }
+        }
+    }
+    wmax = __reduce_max_sync(0xffffffffu, wmax);
+    if (lane == 0 && wmax > 0) atomicMax(&hdr->max_cnt, wmax);
+}
+
+// Records of more than CAP points (rare): one warp each; record + overflow chain gathered into global scratch, ranked
+// into point order there, generic torch.mean row sums.
+__global__ void __launch_bounds__(256)
+fuse_medoid_big_kernel(const float4* __restrict__ records, const int* __restrict__ over_head, const float4* __restrict__ over_ent,
+                       const int* __restrict__ over_next, FuseHdr* hdr, const int2* __restrict__ big_list, float4* scratch,
+                       int2* __restrict__ winners) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nbig = hdr->n_big;
+    for (int bi = blockIdx.x * 8 + warp; bi < nbig; bi += gridDim.x * 8) {
+        const int slot = big_list[bi].x, K = big_list[bi].y;
+        const float4* rec = records + (int64_t)slot * FUSE_STRIDE;
+        int sb = 0;
+        if (lane == 0) sb = atomicAdd(&hdr->scratch_cursor, 2 * K);
+        sb = __shfl_sync(0xffffffffu, sb, 0);
+        float4* raw = scratch + sb;
+        float4* srt = raw + K;
+        raw[lane] = rec[1 + lane];
+        if (lane == 0) {
+            int t = FUSE_CAP;
+            for (int o = over_head[slot]; o != 0 && t < K; o = over_next[o - 1]) raw[t++] = over_ent[o - 1];
+        }
+        __syncwarp();
+        for (int a = lane; a < K; a += 32) {
+            const float4 ea = __ldcg(raw + a);
+            const int v = __float_as_int(ea.w);
+            int rk = 0;
+            for (int t = 0; t < K; ++t) rk += (__float_as_int(__ldcg(raw + t).w) < v) ? 1 : 0;
+            srt[rk] = ea;
+        }
+        __syncwarp();
+        float best = -1e30f; int bk = 0x7fffffff;
+        for (int k = lane; k < K; k += 32) {
+            const float4 me = __ldcg(srt + k);
+            const float sum = mh_torch_inner_sum(K, [&](int t) { return vf_absdot(me, __ldcg(srt + t)); }) / (float)K;
+            if (arg_better_max(sum, k, best, bk)) { best = sum; bk = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (arg_better_max(ob, ok, best, bk)) { best = ob; bk = ok; }
+        }
+        if (lane == 0) winners[slot].x = __float_as_int(__ldcg(srt + bk).w);
+        __syncwarp();
     }
 }
 
-// Pass 3 (per point): drop the point id into its voxel's bucket.
-__global__ void __launch_bounds__(256)
-scatter_kernel(int64_t n, const int* __restrict__ key, const int* __restrict__ rank, const int* __restrict__ cnt,
-               int* __restrict__ bucket) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    bucket[cnt[key[i]] + rank[i]] = (int)i;
-}
-
-// Pass 4: one warp per occupied voxel.  Bucket ids are rank-sorted back into original point order (argmax ties go
-// to the first point) and the medoid under |cos| is taken with torch.mean's summation order
-// (compute_points_similarity, PMVO_utils.py:366-382).  K <= FUSE_FASTK stays in shared memory; larger voxels use the
-// global scratch `sorted` (rare).
-constexpr int FUSE_WARPS = 8, FUSE_FASTK = 64;
-
-__global__ void __launch_bounds__(FUSE_WARPS * 32)
-fuse_medoid_kernel(const int* __restrict__ occ_list, const int* __restrict__ cnt_list, const int* __restrict__ cnt,
-                   const int* __restrict__ hdr, const int* __restrict__ bucket, int* __restrict__ sorted,
-                   const float* __restrict__ dirs, float4* __restrict__ volume) {
-    __shared__ int s_idx_all[FUSE_WARPS][FUSE_FASTK];
-    __shared__ float s_u_all[FUSE_WARPS][FUSE_FASTK * 3];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int M = hdr[0];
-    for (int j = blockIdx.x * FUSE_WARPS + warp; j < M; j += gridDim.x * FUSE_WARPS) {
-        const int g = occ_list[j];
-        const int K = cnt_list[j], base = cnt[g];
-        int bk = 0, best_id;
-        if (K == 1) {
-            best_id = bucket[base];
-        } else if (K <= FUSE_FASTK) {
-            int* s_idx = s_idx_all[warp];
-            float* u = s_u_all[warp];
-            for (int a = lane; a < K; a += 32) {
-                const int v = bucket[base + a];
-                int rank = 0;
-                for (int b = 0; b < K; ++b) rank += (bucket[base + b] < v) ? 1 : 0;
-                s_idx[rank] = v;
-            }
-            __syncwarp();
-            for (int a = lane; a < K; a += 32) {
-                float a0, a1, a2;
-                load_dir(dirs, s_idx[a], a0, a1, a2);
-                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
-                u[3 * a] = a0 / na; u[3 * a + 1] = a1 / na; u[3 * a + 2] = a2 / na;
-            }
-            __syncwarp();
-            float best = -1e30f; bk = 0x7fffffff;
-            for (int k = lane; k < K; k += 32) {
-                const float a0 = u[3 * k], a1 = u[3 * k + 1], a2 = u[3 * k + 2];
-                float sum = mh_torch_inner_sum(K, [&](int t) { return fabsf((a0 * u[3 * t] + a1 * u[3 * t + 1]) + a2 * u[3 * t + 2]); });
-                sum = sum / (float)K;
-                if (sum > best) { best = sum; bk = k; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
-            }
-            best_id = s_idx[bk];
-            __syncwarp();
-        } else {
-            // crowded voxel: same algorithm through global memory
-            for (int a = lane; a < K; a += 32) {
-                const int v = bucket[base + a];
-                int rank = 0;
-                for (int b = 0; b < K; ++b) rank += (bucket[base + b] < v) ? 1 : 0;
-                sorted[base + rank] = v;
-            }
-            __syncwarp();
-            float best = -1e30f; bk = 0x7fffffff;
-            for (int k = lane; k < K; k += 32) {
-                float a0, a1, a2;
-                load_dir(dirs, sorted[base + k], a0, a1, a2);
-                const float na = fmaxf(mh_norm3(a0, a1, a2), 1e-8f);
-                a0 = a0 / na; a1 = a1 / na; a2 = a2 / na;
-                float sum = mh_torch_inner_sum(K, [&](int t) {
-                    float b0, b1, b2;
-                    load_dir(dirs, sorted[base + t], b0, b1, b2);
-                    const float nb = fmaxf(mh_norm3(b0, b1, b2), 1e-8f);
-                    return fabsf((a0 * (b0 / nb) + a1 * (b1 / nb)) + a2 * (b2 / nb)); });
-                sum = sum / (float)K;
-                if (sum > best) { best = sum; bk = k; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
-            }
-            best_id = sorted[base + bk];
-            __syncwarp();
-        }
-        if (lane == 0) {
-            float o0, o1, o2;
-            load_dir(dirs, best_id, o0, o1, o2);
-            volume[g] = make_float4(o0, -o1, -o2, 1.0f);
-        }
+__global__ void __launch_bounds__(64)
+apply_kernel(const int* __restrict__ block_cnt, const int2* __restrict__ winners, const float* __restrict__ dirs,
+             float4* __restrict__ volume) {
+    const int cnt = block_cnt[blockIdx.x];
+    for (int i = threadIdx.x; i < cnt; i += 64) {
+        const int2 w = winners[(int64_t)blockIdx.x * FUSE_BLOCK + i];
+        float o0, o1, o2;
+        load_dir(dirs, w.x, o0, o1, o2);
+        volume[w.y] = make_float4(o0, -o1, -o2, 1.0f);
     }
 }
 
@@ -260,13 +431,10 @@ VGrid make_grid(const double* vmin, double vs, int gx, int gy, int gz) {
 
 }  // namespace
 
-// workspace: [hdr 64 B: #occupied, max count, bucket cursor][cnt nvox][key n][rank n][occ_list n][cnt_list n][bucket n][sorted n]
-extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
-    const int64_t nvox = (int64_t)gx * gy * gz;
-    return 64 + 4 * (nvox + 6 * n + 16);
-}
-
+// per-call workspace: [hdr 64 B][over_head S int][block_cnt nb int][records S*(CAP+1) float4][over_ent n float4]
+// [scratch 2n float4][winners S int2][big_list n/CAP int2][over_next n int] with S = nb * 256 record slots, nb = ceil(n / 256)
 namespace {
+// auxiliary stream for the volume zero fill (one per device and host thread)
 struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 AuxStream& aux_stream() {
     static thread_local AuxStream a[16];
@@ -280,53 +448,87 @@ AuxStream& aux_stream() {
     }
     return x;
 }
+int g_fuse_fill1 = -1;        // tuning state: percentage of the volume zero fill streamed by the bin kernel
+int64_t fuse_nb(int64_t n) { return (n + FUSE_BLOCK - 1) / FUSE_BLOCK; }
 }  // namespace
+extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
+    (void)gx; (void)gy; (void)gz;
+    const int64_t nb = fuse_nb(n), S = nb * FUSE_BLOCK;
+    return 64 + 4 * (S + nb + 16) + 16 * (S * FUSE_STRIDE + 3 * n + 8) + 8 * (S + 2) + 8 * (n / FUSE_CAP + 2) + 4 * (n + 4);
+}
+// persistent plane: 8 B per voxel {count | slot+1}, all-zero between calls
+extern "C" int64_t mh_voxel_fuse_plane_bytes(int32_t gx, int32_t gy, int32_t gz) { return 8 * (int64_t)gx * gy * gz; }
+extern "C" int mh_voxel_fuse_plane_init(void* stream, void* plane, int32_t gx, int32_t gy, int32_t gz) {
+    MH_CHECK_ARG(plane && gx > 0 && gy > 0 && gz > 0, "bad arguments");
+    cudaError_t e = cudaMemsetAsync(plane, 0, (size_t)mh_voxel_fuse_plane_bytes(gx, gy, gz), (cudaStream_t)stream);
+    if (e != cudaSuccess) { mh_set_error("mh_voxel_fuse_plane_init: %s", cudaGetErrorString(e)); return 2; }
+    return 0;
+}
+extern "C" int mh_voxel_fuse_tune(int32_t fill_bin_pct) {
+    MH_CHECK_ARG(fill_bin_pct >= -1 && fill_bin_pct <= 100, "fill share must be a percentage or -1");
+    g_fuse_fill1 = fill_bin_pct;
+    return 0;
+}
 
-extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, int64_t n,
+extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, const uint8_t* valid, int64_t n,
                              const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
-                             void* volume, int32_t* vox_index, void* workspace, int64_t workspace_bytes) {
-    MH_CHECK_ARG(volume && workspace && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
+                             void* volume, int32_t* vox_index, void* plane, void* workspace, int64_t workspace_bytes) {
+    MH_CHECK_ARG(volume && workspace && plane && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
     MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && voxel_size > 0, "bad grid");
-    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31) - 1, "grid or point count too large for int32 keys");
+    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31) - 512, "grid or point count too large for int32 keys");
     MH_CHECK_ARG(workspace_bytes >= mh_voxel_fuse_workspace_bytes(n, gx, gy, gz), "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nvox = (int64_t)gx * gy * gz;
+    float4* vol = reinterpret_cast<float4*>(volume);
+    if (n == 0) {
+        cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, st);
+        MH_CHECK_LAUNCH();
+        return 0;
+    }
+    const int64_t nb = fuse_nb(n), S = nb * FUSE_BLOCK;
     const VGrid g = make_grid(voxel_min_host, voxel_size, gx, gy, gz);
-    int* hdr = reinterpret_cast<int*>(workspace);
-    int* cnt = hdr + 16;
-    int* key = cnt + nvox;
-    int* rank = key + n;
-    int* occ_list = rank + n;
-    int* cnt_list = occ_list + n;
-    int* bucket = cnt_list + n;
-    int* sorted = bucket + n;
-    // The 16 B/voxel zero fill of the volume (the bandwidth-bound part) runs on an auxiliary stream, concurrently
-    // with the latency-bound bucket construction; the two join before the per-voxel results are written.
-    AuxStream& ax = aux_stream();
-    cudaEventRecord(ax.fork, st);
-    cudaStreamWaitEvent(ax.s, ax.fork, 0);
-    cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, ax.s);
-    cudaEventRecord(ax.join, ax.s);
-    cudaMemsetAsync(hdr, 0, 64, st);
-    if (n > 0) {
-        cudaMemsetAsync(cnt, 0, sizeof(int) * nvox, st);
-        const unsigned nb = (unsigned)((n + 255) / 256);
-        count_kernel_vf<<<nb, 256, 0, st>>>(g, points, n, cnt, key, rank, occ_list, hdr, vox_index);
-        MH_COUNT_LAUNCH();
-        bucket_kernel<<<(unsigned)std::min<int64_t>(nb, (int64_t)mh_sm_count() * 8), 256, 0, st>>>(occ_list, cnt, cnt_list, hdr);
-        MH_COUNT_LAUNCH();
-        scatter_kernel<<<nb, 256, 0, st>>>(n, key, rank, cnt, bucket);
-        MH_COUNT_LAUNCH();
+    FuseHdr* hdr = reinterpret_cast<FuseHdr*>(workspace);
+    int* over_head = reinterpret_cast<int*>(hdr + 1);
+    int* block_cnt = over_head + S;
+    float4* records = reinterpret_cast<float4*>(block_cnt + ((nb + 3) / 4) * 4);
+    float4* over_ent = records + S * FUSE_STRIDE;
+    float4* scratch = over_ent + (n + 1);
+    int2* winners = reinterpret_cast<int2*>(scratch + (2 * n + 2));
+    int2* big_list = winners + (S + 2);                             // at most n / CAP records overflow
+    int* over_next = reinterpret_cast<int*>(big_list + (n / FUSE_CAP + 2));
+    u64* pl = reinterpret_cast<u64*>(plane);
+    // Zero fill of the volume (the only bandwidth-sized term): by default a memset on an auxiliary stream that runs
+    // concurrently with the latency-bound binning and the issue-bound medoid kernel and joins before the results are
+    // applied; alternatively (tuning) streamed by the threads of those two kernels themselves.
+    const bool aux_fill = g_fuse_fill1 < 0;
+    AuxStream* ax = nullptr;
+    if (aux_fill) {
+        ax = &aux_stream();
+        cudaEventRecord(ax->fork, st);
+        cudaStreamWaitEvent(ax->s, ax->fork, 0);
+        cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, ax->s);
+        cudaEventRecord(ax->join, ax->s);
     }
-    cudaStreamWaitEvent(st, ax.join, 0);
-    if (n > 0) {
-        int64_t blocks = (n + FUSE_WARPS - 1) / FUSE_WARPS;
-        const int64_t cap = (int64_t)mh_sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        fuse_medoid_kernel<<<(unsigned)blocks, FUSE_WARPS * 32, 0, st>>>(occ_list, cnt_list, cnt, hdr, bucket, sorted, dirs,
-                                                                        reinterpret_cast<float4*>(volume));
-        MH_COUNT_LAUNCH();
-    }
+    cudaMemsetAsync(hdr, 0, sizeof(FuseHdr) + sizeof(int) * (S + nb), st);  // header, overflow chain heads, per-block record counts
+    const int64_t sms = mh_sm_count();
+    const int64_t split = aux_fill ? 0 : nvox * g_fuse_fill1 / 100;
+    const int64_t fill_end = aux_fill ? 0 : nvox;
+    bin_kernel<<<(unsigned)std::max(nb, split > 0 ? sms * 8 : nb), FUSE_BLOCK, 0, st>>>(g, 1.0 / voxel_size, points, dirs, valid, n, pl, records, over_head,
+                                                                                       over_ent, over_next, block_cnt, hdr, vox_index, vol, split);
+    MH_COUNT_LAUNCH();
+    int per_sm = 4;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fuse_medoid_kernel, MEDOID_WARPS * 32, 0);
+    const int64_t items = nb * MEDOID_SPLIT;
+    int64_t mblocks = std::min<int64_t>((items + MEDOID_WARPS - 1) / MEDOID_WARPS, sms * std::max(per_sm, 1));
+    if (split < fill_end) mblocks = std::max<int64_t>(mblocks, sms * 2);
+    fuse_medoid_kernel<<<(unsigned)mblocks, MEDOID_WARPS * 32, 0, st>>>(nb, block_cnt, records, hdr, big_list, pl, winners, vol, split, fill_end);
+    MH_COUNT_LAUNCH();
+    fuse_medoid_big_kernel<<<(unsigned)std::min<int64_t>(sms * 4, n / (8 * FUSE_CAP) + 1), 256, 0, st>>>(records, over_head, over_ent, over_next, hdr,
+                                                                                                  big_list, scratch, winners);
+    MH_COUNT_LAUNCH();
+    if (aux_fill) cudaStreamWaitEvent(st, ax->join, 0);
+    apply_kernel<<<(unsigned)nb, 64, 0, st>>>(block_cnt, winners, dirs, vol);
+    MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
@@ -335,7 +537,7 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
  * call on this workspace (informational: crowded voxels take the global-memory path of fuse_medoid_kernel). */
 extern "C" int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host) {
     MH_CHECK_ARG(workspace && max_k_host, "null pointer");
-    cudaError_t e = cudaMemcpy(max_k_host, reinterpret_cast<const int*>(workspace) + 1, 4, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(max_k_host, &reinterpret_cast<const FuseHdr*>(workspace)->max_cnt, 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { mh_set_error("mh_voxel_fuse_max_points: %s", cudaGetErrorString(e)); return 2; }
     return 0;
 }

@@ -125,20 +125,22 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
     return o, l
 
 
-def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE):
+def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE, valid=None):
     """Voxel fusion; with several ranks each fuses the points whose voxel z-slab it owns into a zeroed volume and
-    the volumes are summed with one all-reduce over NVLink."""
+    the volumes are summed with one all-reduce over NVLink.  `valid` masks points out without compacting them."""
     dev = pm.device
     dist = _dist()
     if dist is None:
-        return P.voxel_fuse(pts, dirs, dev, grid, voxel_min, voxel_size)
+        return P.voxel_fuse(pts, dirs, dev, grid, voxel_min, voxel_size, valid=valid)
     r, w = dist.get_rank(), dist.get_world_size()
     gz = int(grid[2])
     # owner by z slab of the voxel index; float64 index math identical to p2v (points[:,2] flipped)
     z = torch.round((-(pts[:, 2].double()) - float(voxel_min[2])) / float(voxel_size)).clamp_(0, gz - 1).long()
     za, zb = _shard(gz, r, w)
     mine = (z >= za) & (z < zb)
-    vol = P.voxel_fuse(pts[mine].contiguous(), dirs[mine].contiguous(), dev, grid, voxel_min, voxel_size)
+    if valid is not None:
+        mine &= valid.bool()
+    vol = P.voxel_fuse(pts, dirs, dev, grid, voxel_min, voxel_size, valid=mine)
     dist.all_reduce(vol, op=dist.ReduceOp.SUM)
     return vol
 
@@ -165,13 +167,21 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
         nbr = knn_stage(sp, fu, 100, dev)
         fh = head_filter_stage(pm, fu, pm.visible_threshold)
         center = P.medoid_gather(so, nbr, dev)
+        # the head-filtered points are masked out of the fusion instead of being compacted away first: the compaction
+        # needs a host synchronisation, which would expose the launch latency of the whole fusion
+        all_p, all_o = torch.cat([sp, fu], 0), torch.cat([so, center], 0)
+        valid = torch.cat([torch.ones(sp.size(0), dtype=torch.bool, device=dev), ~fh], 0)
+    else:
+        fh = center = None
+        all_p, all_o, valid = sp, so, None
+    mark("unvisible")
+    vol = fuse_stage(pm, all_p, all_o, valid=valid)
+    mark("fuse")
+    if center is not None:
         fo, fp = center[~fh], fu[~fh]
     else:
         fo, fp = so.new_zeros((0, 3)), so.new_zeros((0, 3))
-    all_p, all_o = torch.cat([sp, fp], 0), torch.cat([so, fo], 0)
-    mark("unvisible")
-    vol = fuse_stage(pm, all_p, all_o)
-    mark("fuse")
+    mark("finish")
     out = {"volume": vol, "surface": surface, "filter": filt, "select_p": pts, "select_o": ori, "min_loss": loss,
            "high_conf": hc, "refine_o": o2, "refine_loss": l2, "fu_points": fp, "fu_ori": fo,
            "n_optimized": int(pts.size(0)), "n_selected": int(sp.size(0))}

@@ -398,8 +398,29 @@ def medoid_gather(ori, nbr, dev):
     return out
 
 
-def voxel_fuse(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, voxel_size=VOXEL_SIZE, return_index=False):
-    """PMVO.py:695-726 on the device -> float4 volume [gz,gy,gx,4] (see include/monohair_b200.h)."""
+_FUSE_PLANES = {}          # (device, grid) -> persistent int32 plane of mh_voxel_fuse (all-zero between calls)
+
+
+def fuse_plane(dev, grid):
+    dev = torch.device(dev)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    gx, gy, gz = [int(g) for g in grid]
+    key = (dev.index, gx, gy, gz)
+    pl = _FUSE_PLANES.get(key)
+    if pl is None:
+        pl = torch.empty((lib().mh_voxel_fuse_plane_bytes(gx, gy, gz),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mh_voxel_fuse_plane_init(stream_ptr(dev), ptr(pl), gx, gy, gz), "mh_voxel_fuse_plane_init")
+        _FUSE_PLANES[key] = pl
+    return key, pl
+
+
+def voxel_fuse(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, voxel_size=VOXEL_SIZE, return_index=False,
+               valid=None):
+    """PMVO.py:695-726 on the device -> float4 volume [gz,gy,gx,4] (see include/monohair_b200.h).  `valid` (optional
+    bool/uint8 [n] device tensor): points with a zero entry are skipped, which saves the caller a compaction (and
+    the host synchronisation it implies) right before the fusion."""
     pts = torch.as_tensor(select_points).to(dev).type(torch.float).contiguous()
     dirs = torch.as_tensor(select_ori).to(dev).type(torch.float).contiguous()
     n = pts.size(0)
@@ -409,9 +430,18 @@ def voxel_fuse(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, v
     wsb = lib().mh_voxel_fuse_workspace_bytes(n, gx, gy, gz)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
     vmin = np.ascontiguousarray(np.asarray(voxel_min, dtype=np.float64))
-    with torch.cuda.device(dev):
-        check(lib().mh_voxel_fuse(stream_ptr(dev), ptr(pts), ptr(dirs), n, vmin.ctypes.data_as(C.c_void_p),
-                                  float(voxel_size), gx, gy, gz, ptr(vol), ptr(vidx), ptr(ws), wsb), "mh_voxel_fuse")
+    key, plane = fuse_plane(pts.device, grid)
+    if valid is not None:
+        valid = valid.to(dev).to(torch.uint8).contiguous()
+        assert valid.numel() == n
+    try:
+        with torch.cuda.device(dev):
+            check(lib().mh_voxel_fuse(stream_ptr(dev), ptr(pts), ptr(dirs), ptr(valid), n, vmin.ctypes.data_as(C.c_void_p),
+                                      float(voxel_size), gx, gy, gz, ptr(vol), ptr(vidx), ptr(plane), ptr(ws), wsb),
+                  "mh_voxel_fuse")
+    except Exception:
+        _FUSE_PLANES.pop(key, None)          # the plane may be dirty: a fresh one is zeroed on the next call
+        raise
     return (vol, vidx) if return_index else vol
 
 

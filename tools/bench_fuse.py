@@ -23,29 +23,46 @@ def main():
     n = pts.size(0)
     gx, gy, gz = P.GRID
     vol = torch.empty((gz, gy, gx, 4), dtype=torch.float32, device=dev)
-    wsb = lib().mh_voxel_fuse_workspace_bytes(n, gx, gy, gz)
-    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    _, plane = P.fuse_plane(dev, P.GRID)
     vmin = np.ascontiguousarray(P.VOXEL_MIN)
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
-
-    def run():
-        check(lib().mh_voxel_fuse(stream_ptr(dev), ptr(pts), ptr(dirs), n, vmin.ctypes.data_as(C.c_void_p), float(P.VOXEL_SIZE),
-                                  gx, gy, gz, ptr(vol), None, ptr(ws), wsb), "mh_voxel_fuse")
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(10):
-        flush.zero_()                                  # flush L2 (126 MB) between iterations
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); run(); e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = float(np.median(ts))
     nvox = gx * gy * gz
     alg = n * 28 + n * 16 + nvox * 16
-    occ = int(vol[..., 3].sum().item())
-    print(f"voxel_fuse: n={n} occupied={occ} median {ms*1e3:.1f} us  algorithmic {alg/1e6:.1f} MB -> {alg/ms/1e6:.0f} GB/s")
+    caps = (-1, 0, 25) if "--sweep" in sys.argv else (-1,)
+    if "--fill" in sys.argv:
+        caps = (int(sys.argv[sys.argv.index("--fill") + 1]),)
+    ref = None
+    for cap in caps:
+        check(lib().mh_voxel_fuse_tune(cap), "tune")
+        wsb = lib().mh_voxel_fuse_workspace_bytes(n, gx, gy, gz)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+
+        def run():
+            check(lib().mh_voxel_fuse(stream_ptr(dev), ptr(pts), ptr(dirs), None, n, vmin.ctypes.data_as(C.c_void_p), float(P.VOXEL_SIZE),
+                                      gx, gy, gz, ptr(vol), None, ptr(plane), ptr(ws), wsb), "mh_voxel_fuse")
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            flush.zero_()                                  # flush L2 (126 MB) between iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        occ = int(vol[..., 3].sum().item())
+        clean = int(plane.view(torch.int64).abs().max().item()) == 0
+        hdr = ws[:64].view(torch.int32).cpu().numpy()
+        same = True
+        if ref is None:
+            ref = vol.clone()
+        else:
+            same = bool(torch.equal(ref, vol))
+        print(f"voxel_fuse fill_bin={cap}%: n={n} occupied={occ} max/voxel={hdr[1]} overflow={hdr[2]} median {ms*1e3:.1f} us min {min(ts)*1e3:.1f} us  "
+              f"algorithmic {alg/1e6:.1f} MB -> {alg/ms/1e6:.0f} GB/s = {alg/ms/1e6/6553:.1%} of 6553  plane_clean={clean} same_volume={same}")
+        del ws
+    check(lib().mh_voxel_fuse_tune(-1), "tune")
 
 
 if __name__ == "__main__":
