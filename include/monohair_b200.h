@@ -139,6 +139,13 @@ int mh_refine_update(void* stream, const float* center, const float* upd_loss, c
  * where |cos| < 0.95 -- later chunks see earlier chunks' updates (Gauss-Seidel across chunks).  Runs as one
  * persistent dependency-ordered sweep kernel + one re-score launch over all points (see pmvo_refine.cu). */
 int64_t mh_refine_chunks_workspace_bytes(int64_t n, int64_t sub_num);
+/* The same pass as separate steps (a multi-GPU host replicates the sweep and shards the re-score over ranks):
+ * mh_refine_sweep: ori [n][3] (input, untouched) -> ori_new [n][3] (updated orientations) and center [n][3] (medoids);
+ * then mh_pmvo_refine_loss(points, center) -> upd; then mh_refine_finish(upd, head_filter) -> loss. */
+int64_t mh_refine_sweep_workspace_bytes(int64_t n, int64_t sub_num);
+int mh_refine_sweep(void* stream, const float* ori, const int32_t* nbr, int32_t K, int64_t n, int64_t sub_num,
+                    float* ori_new, float* center, void* scratch, int64_t scratch_bytes);
+int mh_refine_finish(void* stream, const float* upd_loss, const uint8_t* head_filter, int64_t n, float* loss);
 int mh_refine_chunks(void* stream, const mh_views* views, const float* points, const int32_t* nbr, int32_t K,
                      const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
                      float* ori /*in/out*/, float* loss /*out*/, void* scratch, int64_t scratch_bytes);

@@ -46,6 +46,9 @@ _SIGS = {
     "mh_centre_gather": (C.c_int, [p, VP, p, i64, p, p, p, p, p]),
     "mh_refine_chunks": (C.c_int, [p, VP, p, p, i32, p, i64, i64, f32, p, p, p, i64]),
     "mh_refine_chunks_workspace_bytes": (i64, [i64, i64]),
+    "mh_refine_sweep_workspace_bytes": (i64, [i64, i64]),
+    "mh_refine_sweep": (C.c_int, [p, p, p, i32, i64, i64, p, p, p, i64]),
+    "mh_refine_finish": (C.c_int, [p, p, p, i64, p]),
     "mh_refine_update": (C.c_int, [p, p, p, p, i64, p, p]),
     "mh_pmvo_optimize_workspace_bytes": (i64, [VP, i64]),
     "mh_pmvo_optimize": (C.c_int, [p, VP, p, i64, p, i32, f32, p, p, p, p, p, p, p, p, p, i64]),

@@ -686,15 +686,16 @@ extern "C" int mh_refine_update(void* stream, const float* center, const float* 
 //
 // Dependency analysis: the re-score of chunk c reads only (points, centre_c) and feeds nothing back into later
 // chunks; only the orientation update does.  So the sequential part is the medoid + update chain alone:
-//   1. refine_sweep_kernel: ONE persistent launch.  Warps draw point tickets in index order; a warp whose point lies
+//   1. refine_sweep_kernel: ONE persistent launch.  CTAs draw point tickets in index order; a CTA whose point lies
 //      in chunk c waits until chunk c-1 has retired (per-chunk completion counters, acquire/release through L2), then
 //      gathers neighbour j from `ori_new` if j's chunk is earlier than c and from the untouched input otherwise --
 //      exactly the values the reference's in-place array holds when it processes chunk c.  Tickets are drawn in order
-//      and a warp only ever waits on earlier tickets, which are held by running warps: no deadlock for any grid size.
+//      and a CTA only ever waits on earlier tickets, which are held by running CTAs: no deadlock for any grid size.
+//      Four warps share one point so that the hand-over between chunks costs a quarter of a warp-per-point medoid.
 //   2. one mh_pmvo_refine_loss launch over all n points with the stored centres;
-//   3. refine_finish_kernel: loss rules (head filter / -1 -> 0.5, PMVO.py:92, :639) and ori <- ori_new.
+//   3. refine_finish_kernel: loss rules (head filter / -1 -> 0.5, PMVO.py:92, :639).
 namespace {
-constexpr int SW_WARPS = 8;
+constexpr int SW_THREADS = 128;                       // one CTA per point: the chunk hand-over costs one point's latency
 
 MH_D int sw_ld_acquire(const int* p) {
     int v;
@@ -706,44 +707,43 @@ MH_D void sw_red_release(int* p, int v) {
 }
 
 // ctl: [0] next ticket, [16 + c] retired points of chunk c
-__global__ void __launch_bounds__(SW_WARPS * 32)
+__global__ void __launch_bounds__(SW_THREADS)
 refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int* __restrict__ nbr, int64_t n, int K,
                     int sub_num, float* __restrict__ center, int* ctl) {
-    extern __shared__ float4 sw_sh[];                    // [SW_WARPS][K] unit directions (w unused)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4* u = sw_sh + (size_t)warp * K;
+    extern __shared__ float4 sw_u[];                     // [K] unit directions (w unused)
+    __shared__ int s_ticket;
+    __shared__ float s_best[SW_THREADS / 32];
+    __shared__ int s_bk[SW_THREADS / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int* done = ctl + 16;
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(ctl, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
+        if (tid == 0) s_ticket = atomicAdd(ctl, 1);
+        __syncthreads();
+        const int t = s_ticket;
         if (t >= n) break;
         const int64_t i = t;
         const int c = t / sub_num;
         const int first = c * sub_num;                   // neighbours below `first` belong to earlier chunks
-        // neighbour ids first (independent of the wait), then wait for the previous chunk to retire
-        int r[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int k = lane + 32 * q; r[q] = (k < K) ? nbr[i * K + k] : 0; }
-        if (c > 0) {
-            while (sw_ld_acquire(done + c - 1) < sub_num) __nanosleep(200);
+        // neighbour id first (independent of the wait), then wait for the previous chunk to retire
+        const int r0 = (tid < K) ? nbr[i * K + tid] : 0;
+        if (c > 0 && tid == 0) {
+            while (sw_ld_acquire(done + c - 1) < sub_num) __nanosleep(100);
         }
-        auto stage = [&](int k, int rr) {
+        __syncthreads();
+        for (int k = tid; k < K; k += SW_THREADS) {
+            const int rr = (k == tid) ? r0 : nbr[i * K + k];
             const float* src = (rr < first) ? ori_new : ori_old;
             const float a = __ldcg(src + 3 * (int64_t)rr), b = __ldcg(src + 3 * (int64_t)rr + 1), cc = __ldcg(src + 3 * (int64_t)rr + 2);
             const float nn = fmaxf(mh_norm3(a, b, cc), 1e-8f);
-            u[k] = make_float4(a / nn, b / nn, cc / nn, 0.0f);
-        };
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int k = lane + 32 * q; if (k < K) stage(k, r[q]); }
-        for (int k = lane + 128; k < K; k += 32) stage(k, nbr[i * K + k]);
-        __syncwarp();
+            sw_u[k] = make_float4(a / nn, b / nn, cc / nn, 0.0f);
+        }
+        __syncthreads();
         float best = -1e30f; int bk = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
-            const float4 w = u[k];
-            float s = mh_torch_inner_sum(K, [&](int j) { const float4 v = u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
-            s = s / (float)K;
-            if (s > best) { best = s; bk = k; }          // ascending k: first maximum kept
+        for (int k = tid; k < K; k += SW_THREADS) {
+            const float4 w = sw_u[k];
+            float sm = mh_torch_inner_sum(K, [&](int j) { const float4 v = sw_u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
+            sm = sm / (float)K;
+            if (sm > best) { best = sm; bk = k; }        // ascending k: first maximum kept
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -751,7 +751,14 @@ refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int
             const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
             if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
         }
-        if (lane == 0) {
+        if (lane == 0) { s_best[warp] = best; s_bk[warp] = bk; }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 1; w < SW_THREADS / 32; ++w) {
+                const float ob = s_best[w]; const int ok = s_bk[w];
+                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+            }
             const int rr = nbr[i * K + bk];
             const float* src = (rr < first) ? ori_new : ori_old;
             const float c0 = __ldcg(src + 3 * (int64_t)rr), c1 = __ldcg(src + 3 * (int64_t)rr + 1), c2 = __ldcg(src + 3 * (int64_t)rr + 2);
@@ -763,56 +770,78 @@ refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int
             ori_new[3 * i] = upd ? c0 : o0; ori_new[3 * i + 1] = upd ? c1 : o1; ori_new[3 * i + 2] = upd ? c2 : o2;
             sw_red_release(done + c, 1);
         }
-        __syncwarp();
+        // the next iteration's first barrier (after the ticket draw) orders the reuse of sw_u / s_best
     }
 }
 
-__global__ void refine_finish_kernel(const float* __restrict__ ori_new, const float* __restrict__ upd_loss,
-                                     const uint8_t* __restrict__ head_filter, int64_t n, float* __restrict__ ori,
+__global__ void refine_finish_kernel(const float* __restrict__ upd_loss, const uint8_t* __restrict__ head_filter, int64_t n,
                                      float* __restrict__ loss) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float l = head_filter[i] ? -1.0f : upd_loss[i];              // PMVO.py:92
     if (l == -1.0f) l = 0.5f;                                    // :639
     loss[i] = l;
-    ori[3 * i] = ori_new[3 * i]; ori[3 * i + 1] = ori_new[3 * i + 1]; ori[3 * i + 2] = ori_new[3 * i + 2];
 }
 }  // namespace
 
-// scratch: [center n*3][ori_new n*3][upd n] floats, [ctl 16 + #chunks] ints
-extern "C" int64_t mh_refine_chunks_workspace_bytes(int64_t n, int64_t sub_num) {
+// ---- the three steps as separate entry points (the multi-GPU host shards step 2 over ranks) ----------------------
+extern "C" int64_t mh_refine_sweep_workspace_bytes(int64_t n, int64_t sub_num) {
     const int64_t chunks = sub_num > 0 ? (n + sub_num - 1) / sub_num : 0;
-    return 4 * (7 * n + 16 + chunks + 16);
+    return 4 * (16 + chunks + 16);
+}
+
+extern "C" int mh_refine_sweep(void* stream, const float* ori, const int32_t* nbr, int32_t K, int64_t n, int64_t sub_num,
+                               float* ori_new, float* center, void* scratch, int64_t scratch_bytes) {
+    MH_CHECK_ARG(ori && nbr && ori_new && center && scratch, "null pointer");
+    MH_CHECK_ARG(sub_num > 0 && sub_num < (1ll << 30) && K >= 1 && K <= 1024 && n >= 0 && n < (1ll << 31) - 1, "bad arguments");
+    MH_CHECK_ARG(scratch_bytes >= mh_refine_sweep_workspace_bytes(n, sub_num), "scratch too small");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t chunks = (n + sub_num - 1) / sub_num;
+    int* ctl = reinterpret_cast<int*>(scratch);
+    cudaMemsetAsync(ctl, 0, sizeof(int) * (16 + chunks), st);
+    const size_t smem = sizeof(float4) * (size_t)K;
+    cudaFuncSetAttribute(refine_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_sweep_kernel, SW_THREADS, smem);
+    MH_CHECK_ARG(per_sm >= 1, "K too large for the sweep kernel's shared memory");
+    int64_t blocks = (int64_t)mh_sm_count() * per_sm;
+    if (blocks > n) blocks = n;
+    refine_sweep_kernel<<<(unsigned)blocks, SW_THREADS, smem, st>>>(ori, ori_new, nbr, n, K, (int)sub_num, center, ctl);
+    MH_COUNT_LAUNCH();
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_refine_finish(void* stream, const float* upd_loss, const uint8_t* head_filter, int64_t n, float* loss) {
+    MH_CHECK_ARG(upd_loss && head_filter && loss && n >= 0, "bad arguments");
+    if (n == 0) return 0;
+    refine_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(upd_loss, head_filter, n, loss);
+    MH_COUNT_LAUNCH();
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+// all three in one call.  scratch: [center n*3][ori_new n*3][upd n] floats, [sweep scratch]
+extern "C" int64_t mh_refine_chunks_workspace_bytes(int64_t n, int64_t sub_num) {
+    return 4 * 7 * n + mh_refine_sweep_workspace_bytes(n, sub_num);
 }
 
 extern "C" int mh_refine_chunks(void* stream, const mh_views* vw, const float* points, const int32_t* nbr, int32_t K,
                                 const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
                                 float* ori, float* loss, void* scratch, int64_t scratch_bytes) {
     MH_CHECK_ARG(vw && points && nbr && head_filter && ori && loss && scratch, "null pointer");
-    MH_CHECK_ARG(sub_num > 0 && sub_num < (1ll << 30) && K >= 1 && K <= 1024 && n >= 0 && n < (1ll << 31) - 1, "bad arguments");
+    MH_CHECK_ARG(sub_num > 0 && n >= 0, "bad arguments");
     MH_CHECK_ARG(scratch_bytes >= mh_refine_chunks_workspace_bytes(n, sub_num), "scratch too small");
     if (n == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t chunks = (n + sub_num - 1) / sub_num;
     float* center = reinterpret_cast<float*>(scratch);
     float* ori_new = center + 3 * n;
     float* upd = ori_new + 3 * n;
-    int* ctl = reinterpret_cast<int*>(upd + n);
-    cudaMemsetAsync(ctl, 0, sizeof(int) * (16 + chunks), st);
-    const size_t smem = sizeof(float4) * (size_t)K * SW_WARPS;
-    cudaFuncSetAttribute(refine_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_sweep_kernel, SW_WARPS * 32, smem);
-    MH_CHECK_ARG(per_sm >= 1, "K too large for the sweep kernel's shared memory");
-    int64_t blocks = (int64_t)mh_sm_count() * per_sm;
-    if (blocks > (n + SW_WARPS - 1) / SW_WARPS) blocks = (n + SW_WARPS - 1) / SW_WARPS;
-    refine_sweep_kernel<<<(unsigned)blocks, SW_WARPS * 32, smem, st>>>(ori, ori_new, nbr, n, K, (int)sub_num, center, ctl);
-    MH_COUNT_LAUNCH();
-    MH_CHECK_LAUNCH();
-    int rc = mh_pmvo_refine_loss(stream, vw, points, center, n, conf_threshold, upd);
+    int rc = mh_refine_sweep(stream, ori, nbr, K, n, sub_num, ori_new, center, upd + n, mh_refine_sweep_workspace_bytes(n, sub_num));
+    if (rc == 0) rc = mh_pmvo_refine_loss(stream, vw, points, center, n, conf_threshold, upd);
+    if (rc == 0) rc = mh_refine_finish(stream, upd, head_filter, n, loss);
     if (rc) return rc;
-    refine_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ori_new, upd, head_filter, n, ori, loss);
-    MH_COUNT_LAUNCH();
-    MH_CHECK_LAUNCH();
+    cudaError_t e = cudaMemcpyAsync(ori, ori_new, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) { mh_set_error("mh_refine_chunks: %s", cudaGetErrorString(e)); return 2; }
     return 0;
 }

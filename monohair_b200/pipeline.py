@@ -107,22 +107,34 @@ def head_filter_stage(pm, pts, thr):
 
 def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
     """PMVO.refine step (i).  Position-only work is hoisted out of the chunk loop and sharded over ranks: the kNN
-    and the head filter.  What remains sequential is what the reference makes sequential: medoid of the CURRENT
-    neighbour orientations -> re-score -> in-place update, chunk by chunk (Gauss-Seidel across chunks, §9-R7);
-    it is replicated on every rank (each needs the final arrays)."""
+    and the head filter.  What the reference makes sequential -- the medoid of the CURRENT neighbour orientations and
+    the orientation update, chunk by chunk (Gauss-Seidel across chunks, §9-R7) -- runs as one dependency-ordered sweep
+    kernel, replicated on every rank (each needs the final arrays); the re-scoring of (point, medoid) feeds nothing
+    back into the sweep, so it runs afterwards over all points at once, sharded over ranks."""
     dev = pm.device
     n = pts.size(0)
-    o, l = ori.clone(), loss.clone()
     if n == 0:
-        return o, l
+        return ori.clone(), loss.clone()
     nbr = knn_stage(pts, pts, k, dev)
     filt = head_filter_stage(pm, pts, pm.visible_threshold).to(torch.uint8).contiguous()
-    wsb = lib().mh_refine_chunks_workspace_bytes(n, sub_num)
+    o_in = ori.contiguous()
+    o_new, center = torch.empty_like(o_in), torch.empty_like(o_in)
+    wsb = lib().mh_refine_sweep_workspace_bytes(n, sub_num)
     scratch = torch.empty((wsb,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        check(lib().mh_refine_chunks(stream_ptr(dev), pm._vp(), ptr(pts), ptr(nbr), k, ptr(filt), n, sub_num,
-                                     float(pm.conf_threshold), ptr(o), ptr(l), ptr(scratch), wsb), "mh_refine_chunks")
-    return o, l
+        check(lib().mh_refine_sweep(stream_ptr(dev), ptr(o_in), ptr(nbr), k, n, sub_num, ptr(o_new), ptr(center),
+                                    ptr(scratch), wsb), "mh_refine_sweep")
+    dist = _dist()
+    if dist is None:
+        upd = pm.refine_loss_raw(pts, center)
+    else:
+        r, w = dist.get_rank(), dist.get_world_size()
+        a, b = _shard(n, r, w)
+        upd = _all_gather_rows(pm.refine_loss_raw(pts[a:b].contiguous(), center[a:b].contiguous()), n, w, dist).contiguous()
+    l = torch.empty((n,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().mh_refine_finish(stream_ptr(dev), ptr(upd), ptr(filt), n, ptr(l)), "mh_refine_finish")
+    return o_new, l
 
 
 def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE, valid=None):

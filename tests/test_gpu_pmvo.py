@@ -159,6 +159,32 @@ def test_refine_voxelise_vs_reference_golden(case, tmp_path):
     assert np.all(Ori.reshape(Occ.shape[0], Occ.shape[1], 3, Z).transpose(0, 1, 3, 2)[Occ == 0] == 0)
 
 
+def test_refine_chunks_one_call_equals_staged_pipeline(case):
+    """mh_refine_chunks (sweep + re-score + finish in one C call) == pipeline.refine_stage (the three steps called
+    separately, which is what the multi-GPU host shards); small chunks so that many chunk hand-overs happen."""
+    from monohair_b200 import pipeline
+    from monohair_b200 import pmvo as P
+    from monohair_b200._lib import check, lib, ptr, stream_ptr
+    g, sc, pmvo = case
+    dev = pmvo.device
+    pts = torch.from_numpy(g["fwd_points"].astype(np.float32)).to(dev).contiguous()
+    ori = torch.from_numpy(g["fwd_ori"].astype(np.float32)).to(dev).contiguous()
+    loss = torch.from_numpy(g["fwd_loss"].astype(np.float32)).to(dev).contiguous()
+    n, k, sub = pts.size(0), 100, 37
+    o_ref, l_ref = pipeline.refine_stage(pmvo, pts, ori, loss, sub_num=sub, k=k)
+    nbr = P.knn(pts, pts, k, dev)
+    filt = pmvo.filter_head_points(pts, pmvo.visible_threshold).to(torch.uint8).contiguous()
+    o, l = ori.clone(), loss.clone()
+    wsb = lib().mh_refine_chunks_workspace_bytes(n, sub)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    check(lib().mh_refine_chunks(stream_ptr(dev), pmvo._vp(), ptr(pts), ptr(nbr), k, ptr(filt), n, sub,
+                                 float(pmvo.conf_threshold), ptr(o), ptr(l), ptr(ws), wsb), "mh_refine_chunks")
+    assert torch.equal(o, o_ref) and torch.equal(l, l_ref)
+    # and the sweep really is sequential across chunks: one big chunk (pure Jacobi) gives a different result
+    o_j, _ = pipeline.refine_stage(pmvo, pts, ori, loss, sub_num=n, k=k)
+    assert not torch.equal(o_j, o_ref)
+
+
 def test_voxel_fuse_vs_oracle_exact(case):
     from oracle import pmvo_oracle as O
     from monohair_b200 import pmvo as P
