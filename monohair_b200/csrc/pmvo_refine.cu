@@ -519,21 +519,21 @@ constexpr int MED_WARPS = 4;
 __global__ void __launch_bounds__(MED_WARPS * 32)
 medoid_gather_kernel(const float* __restrict__ ori, const int* __restrict__ nbr, int64_t n, int K,
                      float* __restrict__ out, int* __restrict__ out_k) {
-    extern __shared__ float sh[];                       // [MED_WARPS][K][3] normalised + [K] raw index
+    extern __shared__ float4 med_u[];                   // [MED_WARPS][K] unit directions (one 16 B load per term)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* u = sh + (size_t)warp * K * 3;
+    float4* u = med_u + (size_t)warp * K;
     for (int64_t i = (int64_t)blockIdx.x * MED_WARPS + warp; i < n; i += (int64_t)gridDim.x * MED_WARPS) {
         for (int k = lane; k < K; k += 32) {
             const int r = nbr[i * K + k];
             const float a = ori[3 * r], b = ori[3 * r + 1], c = ori[3 * r + 2];
             const float nn = fmaxf(mh_norm3(a, b, c), 1e-8f);
-            u[3 * k] = a / nn; u[3 * k + 1] = b / nn; u[3 * k + 2] = c / nn;
+            u[k] = make_float4(a / nn, b / nn, c / nn, 0.0f);
         }
         __syncwarp();
         float best = -1e30f; int bk = 0x7fffffff;
         for (int k = lane; k < K; k += 32) {
-            const float a = u[3 * k], b = u[3 * k + 1], c = u[3 * k + 2];
-            float s = mh_torch_inner_sum(K, [&](int j) { return fabsf((a * u[3 * j] + b * u[3 * j + 1]) + c * u[3 * j + 2]); });
+            const float4 w = u[k];
+            float s = mh_torch_inner_sum(K, [&](int j) { const float4 v = u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
             s = s / (float)K;
             if (s > best) { best = s; bk = k; }        // ascending k: first maximum kept
         }
@@ -565,9 +565,11 @@ extern "C" int mh_pmvo_refine_loss(void* stream, const mh_views* vw, const float
     auto kern = vw->P == 7 ? refine_loss_kernel<7> : vw->P == 5 ? refine_loss_kernel<5> : vw->P == 9 ? refine_loss_kernel<9>
                                                                                                     : refine_loss_kernel<0>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int64_t blocks = (N + RL_PTS - 1) / RL_PTS;
-    const int64_t cap = (int64_t)mh_sm_count() * 32;
-    if (blocks > cap) blocks = cap;
+    // One block per RL_PTS consecutive points, no grid-stride loop: blocks are dispatched in index order, so the points
+    // in flight at any time are a contiguous (= spatially coherent) window whose patches stay L2-resident.  A capped,
+    // strided grid lets the resident blocks drift apart over the whole point set and sent ~11 kB per point to DRAM.
+    const int64_t blocks = (N + RL_PTS - 1) / RL_PTS;
+    MH_CHECK_ARG(blocks < (1ll << 31), "too many points for one launch");
     kern<<<(unsigned)blocks, RL_GROUP * RL_PTS, smem, (cudaStream_t)stream>>>(*vw, points, dir, N, conf_threshold, loss);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
@@ -640,7 +642,7 @@ extern "C" int mh_medoid_gather(void* stream, const float* ori, const int32_t* n
                                 float* out, int32_t* out_k) {
     MH_CHECK_ARG(ori && nbr && out && K >= 1 && K <= 1024, "bad arguments");
     if (n == 0) return 0;
-    const size_t smem = sizeof(float) * 3 * K * MED_WARPS;
+    const size_t smem = sizeof(float4) * K * MED_WARPS;
     int64_t blocks = (n + MED_WARPS - 1) / MED_WARPS;
     const int64_t cap = (int64_t)mh_sm_count() * 16;
     if (blocks > cap) blocks = cap;
