@@ -165,10 +165,8 @@ int mh_voxel_fuse(void* stream, const float* points, const float* dirs, const ui
                   const double* voxel_min_host /*[3]*/, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
                   void* volume /*float4 [gz][gy][gx]*/, int32_t* vox_index, void* plane, void* workspace,
                   int64_t workspace_bytes);
-/* Tuning hook for the volume's zero fill: -1 (default) = memset on an auxiliary stream concurrent with the binning and
- * medoid kernels; 0..100 = streamed by those kernels' own threads, that percentage by the binning kernel. */
-int mh_voxel_fuse_tune(int32_t fill_bin_pct);
-/* Synchronous: largest per-voxel point count seen by the last mh_voxel_fuse on this workspace (informational). */
+/* Synchronous, informational: largest per-voxel point count seen by the last mh_voxel_fuse on this workspace if some
+ * voxel held more than 32 points (the slower overflow path), else 0. */
 int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host);
 /* Overwrite voxels with given orientations, last writer wins (raw.npy merge, PMVO.py:747-749). */
 int mh_voxel_overwrite(void* stream, const float* points, const float* dirs, int64_t n,

@@ -61,7 +61,6 @@ _SIGS = {
     "mh_voxel_fuse": (C.c_int, [p, p, p, p, i64, p, f64, i32, i32, i32, p, p, p, p, i64]),
     "mh_voxel_fuse_plane_bytes": (i64, [i32, i32, i32]),
     "mh_voxel_fuse_plane_init": (C.c_int, [p, p, i32, i32, i32]),
-    "mh_voxel_fuse_tune": (C.c_int, [i32]),
     "mh_voxel_fuse_max_points": (C.c_int, [p, p]),
     "mh_voxel_overwrite": (C.c_int, [p, p, p, i64, p, f64, i32, i32, i32, p, p]),
     "mh_volume_to_mat": (C.c_int, [p, p, i32, i32, i32, p, p]),

@@ -40,18 +40,17 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, 
 // ---- fusion passes ---------------------------------------------------------------------------------------
 // Shape of the problem: n points (1.7 M) fall into M occupied voxels (81 k, ~20 points each) of a 12.6 M-voxel grid
 // whose 16 B/voxel zero fill (201 MB) is the only bandwidth-sized term; grouping points by voxel is latency bound
-// (atomics, dependent accesses) and the medoid is instruction bound.  The zero fill is therefore streamed by the threads
-// of the two working kernels (fire-and-forget stores that keep HBM busy while the real work waits on latency / issue):
+// (atomics, dependent accesses) and the medoid is instruction bound.
+//   fill       memset of the volume on an auxiliary stream, concurrent with the binning kernel
 //   K1 bin     per point : p2v key -> ONE 64-bit atomic on the dense `plane` {count | slot+1} gives the arrival rank;
 //                          the voxel's first arrival allocates the voxel's record from its BLOCK's slot range (shared-
 //                          memory counter: no global allocation counter) and publishes the slot in the high word.  The
 //                          point's {unit direction, id} goes into the record: one contiguous run of (1 + CAP) float4 =
-//                          header {key} + CAP entries; arrivals beyond CAP are pushed on a per-voxel chain.  Then the
-//                          thread streams its share of the fill.
-//   K2 medoid  per voxel : one warp per record, lane = candidate; entries rank-sorted back into point order through
-//                          shared memory; medoid under |cos| in torch.mean's summation order; writes the winner
-//                          {point id, voxel key}; resets the voxel's plane entry; streams the rest of the fill.
-//   K3 apply   per record: winner's raw direction -> the (by now completely zeroed) volume.
+//                          header {key} + CAP entries; arrivals beyond CAP are pushed on a per-voxel chain.
+//   K2 medoid  per voxel : (after the fill) one warp per record, lane = candidate; entries rank-sorted back into point
+//                          order through shared memory; medoid under |cos| in torch.mean's summation order; the
+//                          winner's raw direction goes into the volume; the voxel's plane entry is reset.
+//   K3 big     records of more than CAP points (rare), through global scratch.
 // The plane is persistent workspace state: all-zero on entry, all-zero again on exit (only M entries are touched), so
 // no per-call clear of a dense array and no per-point key/rank arrays exist.  HBM traffic ~= points + directions +
 // volume (+ records, mostly L2-resident between the kernels).
@@ -61,16 +60,6 @@ typedef unsigned long long u64;
 constexpr int FUSE_CAP = 32;                 // entries per record
 constexpr int64_t FUSE_STRIDE = FUSE_CAP + 1;
 constexpr int FUSE_BLOCK = 256;              // points per K1 block = record slots owned by the block
-
-__device__ __forceinline__ void fill_zero(float4* __restrict__ vol, int64_t beg, int64_t end) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    int64_t g = beg + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; g + 3 * stride < end; g += 4 * stride) {
-        __stcs(vol + g, z); __stcs(vol + g + stride, z); __stcs(vol + g + 2 * stride, z); __stcs(vol + g + 3 * stride, z);
-    }
-    for (; g < end; g += stride) __stcs(vol + g, z);
-}
 
 // torch.argmax semantics: NaN counts as the maximum, ties go to the lowest index
 __device__ __forceinline__ bool arg_better_max(float s, int k, float best, int bk) {
@@ -109,10 +98,10 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 8)
 bin_kernel(VGrid g, double inv_vs, const float* __restrict__ pts, const float* __restrict__ dirs,
            const uint8_t* __restrict__ valid, int64_t n, u64* plane,
            float4* records, int* over_head, float4* __restrict__ over_ent, int* __restrict__ over_next,
-           int* block_cnt, FuseHdr* hdr, int* __restrict__ vox_index, float4* __restrict__ vol, int64_t fill_end) {
+           int* block_cnt, FuseHdr* hdr, int* __restrict__ vox_index) {
     __shared__ int s_alloc;
     const int64_t i = (int64_t)blockIdx.x * FUSE_BLOCK + threadIdx.x;
-    if ((int64_t)blockIdx.x * FUSE_BLOCK < n) {
+    {
         if (threadIdx.x == 0) s_alloc = 0;
         __syncthreads();
         const int lane = threadIdx.x & 31;
@@ -145,6 +134,7 @@ bin_kernel(VGrid g, double inv_vs, const float* __restrict__ pts, const float* _
             base = (int)(old & 0xffffffffu);
             slot1 = (int64_t)(old >> 32);
             alloc = (base == 0);                         // the voxel's first arrival
+            if (base + npeers > FUSE_CAP) atomicMax(&hdr->max_cnt, base + npeers);   // crowded voxels only (rare)
         }
         // first arrivals take a record from the block's slot range and publish slot+1 in the plane's high word
         const unsigned am = __ballot_sync(0xffffffffu, alloc);
@@ -176,7 +166,6 @@ bin_kernel(VGrid g, double inv_vs, const float* __restrict__ pts, const float* _
             }
         }
     }
-    fill_zero(vol, 0, fill_end);                         // after the ordered part: nothing waits on these stores
 }
 
 // |cos| of two unit vectors as torch.cosine_similarity's dot evaluates it
@@ -187,7 +176,7 @@ __device__ __forceinline__ float vf_absdot(const float4& w, const float4& v) { r
 // floats (mh_torch_sum.cuh): 8 vector-lane accumulators acc[t & 7] over t < 8*(K/8) (for K < 40 the 4 row accumulators
 // collapse to this sequential form), the scalar tail summed first, then the 8 accumulators added in order; K < 8 takes
 // torch's scalar path.  Records of more than CAP points go through global scratch with the generic summation.
-constexpr int MEDOID_WARPS = 8, MEDOID_SPLIT = 16;        // warps per block; warps sharing one K1 block's records
+constexpr int MEDOID_WARPS = 8;                          // one CTA per binning block: its warps share that block's records
 
 // warp arg-max of non-negative (or NaN) means with torch.argmax semantics: positive floats and NaN order like their bit
 // patterns (NaN above everything = counts as the maximum), ties go to the lowest candidate index.
@@ -197,109 +186,108 @@ __device__ __forceinline__ int vf_warp_argmax(float mean, int k, bool valid) {
     return (int)__reduce_min_sync(0xffffffffu, (bits == mx && valid) ? (unsigned)k : 0x7fffffffu);
 }
 
-__global__ void __launch_bounds__(MEDOID_WARPS * 32, 6)
-fuse_medoid_kernel(int64_t n_blocks, const int* __restrict__ block_cnt, const float4* __restrict__ records,
-                   FuseHdr* hdr, int2* __restrict__ big_list, u64* __restrict__ plane, int2* __restrict__ winners,
-                   float4* __restrict__ vol, int64_t fill_beg, int64_t fill_end) {
+// winner's direction -> volume: flip to dir.y <= 0 (PMVO.py:702-703), then the frame HairGrowing works in
+__device__ __forceinline__ void store_winner(float4* __restrict__ volume, int key, float a, float b, float c) {
+    if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
+    volume[key] = make_float4(a, -b, -c, 1.0f);
+}
+
+// CTA b walks the records allocated by binning block b (contiguous slots, so the hardware block scheduler does the load
+// balancing); warp w takes records w, w+8, ...  The next record's header / count / entries are loaded one record
+// ahead, and the winner's raw direction is fetched at the end of a record and stored into the (already zero-filled)
+// volume at the end of the next one, so no load is waited for where it is issued.
+__global__ void __launch_bounds__(MEDOID_WARPS * 32, 5)
+fuse_medoid_kernel(const int* __restrict__ block_cnt, const float4* __restrict__ records, FuseHdr* hdr,
+                   int2* __restrict__ big_list, u64* __restrict__ plane, const float* __restrict__ dirs,
+                   float4* __restrict__ volume) {
     __shared__ float4 s_u[MEDOID_WARPS][FUSE_CAP];
     __shared__ int4 s_ids[MEDOID_WARPS][FUSE_CAP / 4];
-    fill_zero(vol, fill_beg, fill_end);
+    const int cnt = block_cnt[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= cnt) return;
     float4* u = s_u[warp];
     const int4* ids4 = s_ids[warp];
-    int wmax = 0;
-    const int64_t n_items = n_blocks * MEDOID_SPLIT;
-    for (int64_t w = (int64_t)blockIdx.x * MEDOID_WARPS + warp; w < n_items; w += (int64_t)gridDim.x * MEDOID_WARPS) {
-        const int64_t b = w / MEDOID_SPLIT;
-        const int cnt = block_cnt[b];
-        const int r0 = (int)(w % MEDOID_SPLIT);
-        const int mine = (cnt - r0 + MEDOID_SPLIT - 1) / MEDOID_SPLIT;   // this warp's records: r0, r0+SPLIT, ...
-        const float4* rec0 = records + (b * FUSE_BLOCK + r0) * FUSE_STRIDE;
-        for (int c0 = 0; c0 < mine; c0 += 32) {
-            // batch: lane i fetches {key, count} of record c0+i (the two dependent loads of every record, all in flight
-            // together), the record loop below broadcasts them
-            int my_key = 0, my_K = 0;
-            if (c0 + lane < mine) {
-                my_key = reinterpret_cast<const int*>(rec0 + (int64_t)(c0 + lane) * MEDOID_SPLIT * FUSE_STRIDE)[0];
-                my_K = (int)(__ldcg(plane + my_key) & 0xffffffffu);
+    const float4* rec = records + ((int64_t)blockIdx.x * FUSE_BLOCK + warp) * FUSE_STRIDE;
+    constexpr int64_t STEP = MEDOID_WARPS * FUSE_STRIDE;
+    // software pipeline: {key, K, e} of the current record were loaded during the previous one
+    int key_n = reinterpret_cast<const int*>(rec)[0];
+    float4 e_n = rec[1 + lane];
+    int K_n = (int)(__ldcg(plane + key_n) & 0xffffffffu);
+    bool pend = false;                                   // lane 0: a winner whose direction load is in flight
+    int pend_key = 0;
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+    for (int ri = warp; ri < cnt; ri += MEDOID_WARPS, rec += STEP) {
+        const int key = key_n, K = K_n;
+        const float4 e = e_n;
+        const bool more = ri + MEDOID_WARPS < cnt;
+        if (more) {
+            key_n = reinterpret_cast<const int*>(rec + STEP)[0];
+            e_n = rec[STEP + 1 + lane];
+        }
+        int best_id = -1;
+        if (K <= FUSE_CAP) {
+            const int id = (lane < K) ? __float_as_int(e.w) : 0x7fffffff;
+            reinterpret_cast<int*>(s_ids[warp])[lane] = id;
+            __syncwarp();
+            int rk = 0;                                  // rank = number of smaller ids in the record
+            for (int t4 = 0; 4 * t4 < K; ++t4) {
+                const int4 v = ids4[t4];
+                rk += (v.x < id) + (v.y < id) + (v.z < id) + (v.w < id);
             }
-            const int nrec = min(32, mine - c0);
-            float4 e_next = rec0[(int64_t)c0 * MEDOID_SPLIT * FUSE_STRIDE + 1 + lane];
-            for (int c = 0; c < nrec; ++c) {
-                const int64_t ri = (int64_t)(c0 + c) * MEDOID_SPLIT;
-                const float4* rec = rec0 + ri * FUSE_STRIDE;
-                const int64_t slot = b * FUSE_BLOCK + r0 + ri;
-                const float4 e = e_next;
-                if (c + 1 < nrec) e_next = rec[MEDOID_SPLIT * FUSE_STRIDE + 1 + lane];       // next record's entries
-                const int key = __shfl_sync(0xffffffffu, my_key, c);
-                const int K = __shfl_sync(0xffffffffu, my_K, c);
-                wmax = max(wmax, K);
-                int best_id;
-                if (K <= FUSE_CAP) {
-                    const int id = (lane < K) ? __float_as_int(e.w) : 0x7fffffff;
-                    reinterpret_cast<int*>(s_ids[warp])[lane] = id;
-                    __syncwarp();
-                    int rk = 0;                                         // rank = number of smaller ids in the record
-                    for (int t4 = 0; 4 * t4 < K; ++t4) {
-                        const int4 v = ids4[t4];
-                        rk += (v.x < id) + (v.y < id) + (v.z < id) + (v.w < id);
-                    }
-                    if (lane < K) u[rk] = e;
-                    __syncwarp();
-                    const float4 me = u[min(lane, K - 1)];              // candidate = sorted position `lane`
-                    float total;
-                    if (K < 8) {
-                        // torch's scalar path: 4 accumulators over rows of 4, leftovers into the first, then p0+p1+p2+p3
-                        float x[7];
+            if (lane < K) u[rk] = e;
+            __syncwarp();
+            const float4 me = u[min(lane, K - 1)];       // candidate = sorted position `lane`
+            float total;
+            if (K < 8) {
+                // torch's scalar path: 4 accumulators over rows of 4, leftovers into the first, then p0+p1+p2+p3
+                float x[7];
 #pragma unroll
-                        for (int t = 0; t < 7; ++t) x[t] = (t < K) ? vf_absdot(me, u[t]) : 0.0f;
-                        if (K >= 4) {
-                            float p0 = 0.0f + x[0];
-                            const float p1 = 0.0f + x[1], p2 = 0.0f + x[2], p3 = 0.0f + x[3];
+                for (int t = 0; t < 7; ++t) x[t] = (t < K) ? vf_absdot(me, u[t]) : 0.0f;
+                if (K >= 4) {
+                    float q0 = 0.0f + x[0];
+                    const float q1 = 0.0f + x[1], q2 = 0.0f + x[2], q3 = 0.0f + x[3];
 #pragma unroll
-                            for (int t = 4; t < 7; ++t) if (t < K) p0 += x[t];
-                            p0 += p1; p0 += p2; p0 += p3;
-                            total = p0;
-                        } else {
-                            total = 0.0f;
-#pragma unroll
-                            for (int t = 0; t < 3; ++t) if (t < K) total += x[t];
-                        }
-                    } else {
-                        const int nv8 = K & ~7;
-                        float acc[8];
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
-                        for (int t0 = 0; t0 < nv8; t0 += 8) {
-#pragma unroll
-                            for (int l = 0; l < 8; ++l) acc[l] += vf_absdot(me, u[t0 + l]);
-                        }
-                        total = 0.0f;
-                        for (int t = nv8; t < K; ++t) total += vf_absdot(me, u[t]);
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) total += acc[l];
-                    }
-                    const int bk = vf_warp_argmax(total / (float)K, lane, lane < K);
-                    best_id = __float_as_int(u[bk].w);
-                    __syncwarp();
+                    for (int t = 4; t < 7; ++t) if (t < K) q0 += x[t];
+                    q0 += q1; q0 += q2; q0 += q3;
+                    total = q0;
                 } else {
-                    // crowded voxel: left to fuse_medoid_big_kernel (keeps this kernel's register count low)
-                    if (lane == 0) {
-                        big_list[atomicAdd(&hdr->n_big, 1)] = make_int2((int)slot, K);
-                        plane[key] = 0ull;
-                        winners[slot] = make_int2(0, key);
-                    }
-                    continue;
+                    total = 0.0f;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) if (t < K) total += x[t];
                 }
-                if (lane == 0) {
-                    winners[slot] = make_int2(best_id, key);
-                    plane[key] = 0ull;                   // leave the plane clean for the next call
+            } else {
+                const int nv8 = K & ~7;
+                float acc[8];
+#pragma unroll
+                for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
+                for (int t0 = 0; t0 < nv8; t0 += 8) {
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) acc[l] += vf_absdot(me, u[t0 + l]);
                 }
+                total = 0.0f;
+                for (int t = nv8; t < K; ++t) total += vf_absdot(me, u[t]);
+#pragma unroll
+                for (int l = 0; l < 8; ++l) total += acc[l];
             }
+            const int bk = vf_warp_argmax(total / (float)K, lane, lane < K);
+            best_id = __float_as_int(u[bk].w);
+            __syncwarp();
+        } else if (lane == 0) {
+            // crowded voxel: left to fuse_medoid_big_kernel (keeps this kernel's register count low)
+            big_list[atomicAdd(&hdr->n_big, 1)] = make_int2((int)((int64_t)blockIdx.x * FUSE_BLOCK + ri), K);
+        }
+        if (more) K_n = (int)(__ldcg(plane + key_n) & 0xffffffffu);      // key_n has had a record's time to arrive
+        if (lane == 0) {
+            if (pend) store_winner(volume, pend_key, p0, p1, p2);
+            pend = best_id >= 0;
+            if (pend) {                                  // raw direction: consumed (flipped, stored) one record later
+                p0 = dirs[3 * best_id]; p1 = dirs[3 * best_id + 1]; p2 = dirs[3 * best_id + 2];
+                pend_key = key;
+            }
+            plane[key] = 0ull;                           // leave the plane clean for the next call
         }
     }
-    wmax = __reduce_max_sync(0xffffffffu, wmax);
-    if (lane == 0 && wmax > 0) atomicMax(&hdr->max_cnt, wmax);
+    if (lane == 0 && pend) store_winner(volume, pend_key, p0, p1, p2);
 }
 
 // Records of more than CAP points (rare): one warp each; record + overflow chain gathered into global scratch, ranked
@@ -307,7 +295,7 @@ fuse_medoid_kernel(int64_t n_blocks, const int* __restrict__ block_cnt, const fl
 __global__ void __launch_bounds__(256)
 fuse_medoid_big_kernel(const float4* __restrict__ records, const int* __restrict__ over_head, const float4* __restrict__ over_ent,
                        const int* __restrict__ over_next, FuseHdr* hdr, const int2* __restrict__ big_list, float4* scratch,
-                       int2* __restrict__ winners) {
+                       const float* __restrict__ dirs, float4* __restrict__ volume) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nbig = hdr->n_big;
     for (int bi = blockIdx.x * 8 + warp; bi < nbig; bi += gridDim.x * 8) {
@@ -344,20 +332,12 @@ fuse_medoid_big_kernel(const float4* __restrict__ records, const int* __restrict
             const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
             if (arg_better_max(ob, ok, best, bk)) { best = ob; bk = ok; }
         }
-        if (lane == 0) winners[slot].x = __float_as_int(__ldcg(srt + bk).w);
+        if (lane == 0) {
+            float o0, o1, o2;
+            load_dir(dirs, __float_as_int(__ldcg(srt + bk).w), o0, o1, o2);
+            volume[reinterpret_cast<const int*>(rec)[0]] = make_float4(o0, -o1, -o2, 1.0f);
+        }
         __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(64)
-apply_kernel(const int* __restrict__ block_cnt, const int2* __restrict__ winners, const float* __restrict__ dirs,
-             float4* __restrict__ volume) {
-    const int cnt = block_cnt[blockIdx.x];
-    for (int i = threadIdx.x; i < cnt; i += 64) {
-        const int2 w = winners[(int64_t)blockIdx.x * FUSE_BLOCK + i];
-        float o0, o1, o2;
-        load_dir(dirs, w.x, o0, o1, o2);
-        volume[w.y] = make_float4(o0, -o1, -o2, 1.0f);
     }
 }
 
@@ -432,7 +412,7 @@ VGrid make_grid(const double* vmin, double vs, int gx, int gy, int gz) {
 }  // namespace
 
 // per-call workspace: [hdr 64 B][over_head S int][block_cnt nb int][records S*(CAP+1) float4][over_ent n float4]
-// [scratch 2n float4][winners S int2][big_list n/CAP int2][over_next n int] with S = nb * 256 record slots, nb = ceil(n / 256)
+// [scratch 2n float4][big_list n/CAP int2][over_next n int] with S = nb * 256 record slots, nb = ceil(n / 256)
 namespace {
 // auxiliary stream for the volume zero fill (one per device and host thread)
 struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
@@ -448,13 +428,12 @@ AuxStream& aux_stream() {
     }
     return x;
 }
-int g_fuse_fill1 = -1;        // tuning state: percentage of the volume zero fill streamed by the bin kernel
 int64_t fuse_nb(int64_t n) { return (n + FUSE_BLOCK - 1) / FUSE_BLOCK; }
 }  // namespace
 extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
     (void)gx; (void)gy; (void)gz;
     const int64_t nb = fuse_nb(n), S = nb * FUSE_BLOCK;
-    return 64 + 4 * (S + nb + 16) + 16 * (S * FUSE_STRIDE + 3 * n + 8) + 8 * (S + 2) + 8 * (n / FUSE_CAP + 2) + 4 * (n + 4);
+    return 64 + 4 * (S + nb + 16) + 16 * (S * FUSE_STRIDE + 3 * n + 8) + 8 * (n / FUSE_CAP + 2) + 4 * (n + 4);
 }
 // persistent plane: 8 B per voxel {count | slot+1}, all-zero between calls
 extern "C" int64_t mh_voxel_fuse_plane_bytes(int32_t gx, int32_t gy, int32_t gz) { return 8 * (int64_t)gx * gy * gz; }
@@ -462,11 +441,6 @@ extern "C" int mh_voxel_fuse_plane_init(void* stream, void* plane, int32_t gx, i
     MH_CHECK_ARG(plane && gx > 0 && gy > 0 && gz > 0, "bad arguments");
     cudaError_t e = cudaMemsetAsync(plane, 0, (size_t)mh_voxel_fuse_plane_bytes(gx, gy, gz), (cudaStream_t)stream);
     if (e != cudaSuccess) { mh_set_error("mh_voxel_fuse_plane_init: %s", cudaGetErrorString(e)); return 2; }
-    return 0;
-}
-extern "C" int mh_voxel_fuse_tune(int32_t fill_bin_pct) {
-    MH_CHECK_ARG(fill_bin_pct >= -1 && fill_bin_pct <= 100, "fill share must be a percentage or -1");
-    g_fuse_fill1 = fill_bin_pct;
     return 0;
 }
 
@@ -493,48 +467,35 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
     float4* records = reinterpret_cast<float4*>(block_cnt + ((nb + 3) / 4) * 4);
     float4* over_ent = records + S * FUSE_STRIDE;
     float4* scratch = over_ent + (n + 1);
-    int2* winners = reinterpret_cast<int2*>(scratch + (2 * n + 2));
-    int2* big_list = winners + (S + 2);                             // at most n / CAP records overflow
+    int2* big_list = reinterpret_cast<int2*>(scratch + (2 * n + 2));       // at most n / CAP records overflow
     int* over_next = reinterpret_cast<int*>(big_list + (n / FUSE_CAP + 2));
     u64* pl = reinterpret_cast<u64*>(plane);
-    // Zero fill of the volume (the only bandwidth-sized term): by default a memset on an auxiliary stream that runs
-    // concurrently with the latency-bound binning and the issue-bound medoid kernel and joins before the results are
-    // applied; alternatively (tuning) streamed by the threads of those two kernels themselves.
-    const bool aux_fill = g_fuse_fill1 < 0;
-    AuxStream* ax = nullptr;
-    if (aux_fill) {
-        ax = &aux_stream();
-        cudaEventRecord(ax->fork, st);
-        cudaStreamWaitEvent(ax->s, ax->fork, 0);
-        cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, ax->s);
-        cudaEventRecord(ax->join, ax->s);
-    }
+    // The zero fill of the volume (201 MB at 256x256x192: the only bandwidth-sized term) is a memset on an auxiliary
+    // stream, concurrent with the latency-bound binning kernel; the medoid kernel, which writes the results into the
+    // volume, joins it first.  (Streaming the fill from the binning / medoid kernels' own threads was measured: it is
+    // additive there, profiles/r1_summary.md.)
+    AuxStream& ax = aux_stream();
+    cudaEventRecord(ax.fork, st);
+    cudaStreamWaitEvent(ax.s, ax.fork, 0);
+    cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, ax.s);
+    cudaEventRecord(ax.join, ax.s);
     cudaMemsetAsync(hdr, 0, sizeof(FuseHdr) + sizeof(int) * (S + nb), st);  // header, overflow chain heads, per-block record counts
-    const int64_t sms = mh_sm_count();
-    const int64_t split = aux_fill ? 0 : nvox * g_fuse_fill1 / 100;
-    const int64_t fill_end = aux_fill ? 0 : nvox;
-    bin_kernel<<<(unsigned)std::max(nb, split > 0 ? sms * 8 : nb), FUSE_BLOCK, 0, st>>>(g, 1.0 / voxel_size, points, dirs, valid, n, pl, records, over_head,
-                                                                                       over_ent, over_next, block_cnt, hdr, vox_index, vol, split);
+    bin_kernel<<<(unsigned)nb, FUSE_BLOCK, 0, st>>>(g, 1.0 / voxel_size, points, dirs, valid, n, pl, records, over_head, over_ent,
+                                                    over_next, block_cnt, hdr, vox_index);
     MH_COUNT_LAUNCH();
-    int per_sm = 4;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fuse_medoid_kernel, MEDOID_WARPS * 32, 0);
-    const int64_t items = nb * MEDOID_SPLIT;
-    int64_t mblocks = std::min<int64_t>((items + MEDOID_WARPS - 1) / MEDOID_WARPS, sms * std::max(per_sm, 1));
-    if (split < fill_end) mblocks = std::max<int64_t>(mblocks, sms * 2);
-    fuse_medoid_kernel<<<(unsigned)mblocks, MEDOID_WARPS * 32, 0, st>>>(nb, block_cnt, records, hdr, big_list, pl, winners, vol, split, fill_end);
+    cudaStreamWaitEvent(st, ax.join, 0);
+    fuse_medoid_kernel<<<(unsigned)nb, MEDOID_WARPS * 32, 0, st>>>(block_cnt, records, hdr, big_list, pl, dirs, vol);
     MH_COUNT_LAUNCH();
-    fuse_medoid_big_kernel<<<(unsigned)std::min<int64_t>(sms * 4, n / (8 * FUSE_CAP) + 1), 256, 0, st>>>(records, over_head, over_ent, over_next, hdr,
-                                                                                                  big_list, scratch, winners);
-    MH_COUNT_LAUNCH();
-    if (aux_fill) cudaStreamWaitEvent(st, ax->join, 0);
-    apply_kernel<<<(unsigned)nb, 64, 0, st>>>(block_cnt, winners, dirs, vol);
+    fuse_medoid_big_kernel<<<(unsigned)std::min<int64_t>((int64_t)mh_sm_count() * 4, n / (8 * FUSE_CAP) + 1), 256, 0, st>>>(
+        records, over_head, over_ent, over_next, hdr, big_list, scratch, dirs, vol);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
 }
 
 /* after synchronising the stream: the largest number of points that fell into one voxel in the last mh_voxel_fuse
- * call on this workspace (informational: crowded voxels take the global-memory path of fuse_medoid_kernel). */
+ * call on this workspace if some voxel held more than 32 (such voxels take the overflow chain and
+ * fuse_medoid_big_kernel), else 0.  Informational. */
 extern "C" int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host) {
     MH_CHECK_ARG(workspace && max_k_host, "null pointer");
     cudaError_t e = cudaMemcpy(max_k_host, &reinterpret_cast<const FuseHdr*>(workspace)->max_cnt, 4, cudaMemcpyDeviceToHost);

@@ -28,12 +28,8 @@ def main():
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
     nvox = gx * gy * gz
     alg = n * 28 + n * 16 + nvox * 16
-    caps = (-1, 0, 25) if "--sweep" in sys.argv else (-1,)
-    if "--fill" in sys.argv:
-        caps = (int(sys.argv[sys.argv.index("--fill") + 1]),)
     ref = None
-    for cap in caps:
-        check(lib().mh_voxel_fuse_tune(cap), "tune")
+    for cap in (0,):
         wsb = lib().mh_voxel_fuse_workspace_bytes(n, gx, gy, gz)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
 
@@ -59,10 +55,9 @@ def main():
             ref = vol.clone()
         else:
             same = bool(torch.equal(ref, vol))
-        print(f"voxel_fuse fill_bin={cap}%: n={n} occupied={occ} max/voxel={hdr[1]} overflow={hdr[2]} median {ms*1e3:.1f} us min {min(ts)*1e3:.1f} us  "
+        print(f"voxel_fuse: n={n} occupied={occ} crowded-max={hdr[1]} overflow={hdr[2]} median {ms*1e3:.1f} us min {min(ts)*1e3:.1f} us  "
               f"algorithmic {alg/1e6:.1f} MB -> {alg/ms/1e6:.0f} GB/s = {alg/ms/1e6/6553:.1%} of 6553  plane_clean={clean} same_volume={same}")
         del ws
-    check(lib().mh_voxel_fuse_tune(-1), "tune")
 
 
 if __name__ == "__main__":
