@@ -271,6 +271,8 @@ def run_b200(args, cfg):
                 "achieved": opt_bytes / (med["optimize"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": opt_bytes / (med["optimize"] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "ms": med["optimize"],
+                "note": "instruction-issue bound: smsp__issue_active 80 %, DRAM 0.2 % of peak (profiles/r1_ncu_full.md); "
+                        "the HBM-bound kernels of the path are listed under hbm_bound_kernels",
                 "hbm_bound_kernels": {
                     "voxel_fuse": {"achieved": fuse_bytes / (med["fuse"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                    "frac": fuse_bytes / (med["fuse"] * 1e-3) / 1e9 / hbm_peak, "ms": med["fuse"]},
@@ -312,6 +314,29 @@ def run_b200(args, cfg):
                "api": "PMVO(camera,depths,Ori,Conf,masks) with the reference loaders' float64/float32 arrays (pinned) + "
                       "filter/forward/refine/fuse; volume and per-point results read back"}
         del h_depth, h_ori, h_conf, h_mask
+        # the same job fed with the maps in their FILE formats (8-bit orientation / confidence / mask images, float32 depth
+        # channel; PMVO.from_u8 decodes them inside the pack kernel): what a pipeline that reads the
+        # stage files directly pays.  Reported beside `e2e`, which keeps the reference loaders' float64 arrays.
+        if torch.is_tensor(sc.depth):
+            u_depth, u_ori, u_conf, u_mask = [t.cpu().contiguous().pin_memory() for t in (sc.depth, sc.ori_gray, sc.conf_u8, sc.mask_u8)]
+        else:
+            u_depth, u_ori, u_conf, u_mask = [pin(a) for a in (sc.depth, sc.ori_gray, sc.conf_u8, sc.mask_u8)]
+        h2d_u8 = sum(t.numel() * t.element_size() for t in (u_depth, u_ori, u_conf, u_mask)) + h_cand.numel() * h_cand.element_size()
+        torch.cuda.empty_cache()
+        host = pipeline.pmvo_job_host(cams, u_depth, u_ori, u_conf, u_mask, h_cand, u8=True, **kw2)                 # warm-up
+        barrier()
+        t0 = time.time()
+        for _ in range(n_e2e):
+            host = pipeline.pmvo_job_host(cams, u_depth, u_ori, u_conf, u_mask, h_cand, u8=True, **kw2)
+        barrier()
+        t_u8 = (time.time() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([t_u8], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_u8 = float(t.item())
+        e2e["file_format_maps"] = {"value": host["n_optimized"] / t_u8, "unit": "points/s", "h2d_bytes_per_step": int(h2d_u8),
+                                   "s_per_step": t_u8, "api": "PMVO.from_u8(camera, depth f32, best_ori u8, conf u8, mask u8)"}
+        del u_depth, u_ori, u_conf, u_mask
 
     # ---- CPU baseline (rank 0, N=1) --------------------------------------------------------------------------
     cpu = None

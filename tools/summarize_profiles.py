@@ -1,6 +1,6 @@
 """Turn the ncu artefacts brought back in gpurun_out/ into the committed summaries under profiles/.
 
-    python tools/summarize_profiles.py <round-tag> <launches.csv> <full.ncu-rep> <workload-name> <points-per-launch>
+    python tools/summarize_profiles.py <round-tag> <launches.csv> <full.ncu-rep>[,<more.ncu-rep>] <workload-name> <points-per-launch> [kernels,to,drop]
 """
 import collections
 import csv
@@ -55,21 +55,27 @@ def launches(path, out_md):
     return agg, tot
 
 
-def full(rep, out_md):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    ik = hdr.index("Kernel Name")
+def full(reps, out_md, drop=()):
+    """reps: comma-separated .ncu-rep files; kernels of later files replace same-named ones of earlier files."""
     res = {}
-    for r in rows[2:]:
-        name = short(r[ik])
-        if name in res:
-            continue
-        d = {}
-        for k in KEYS:
-            if k in hdr:
-                d[k] = (r[hdr.index(k)], units[hdr.index(k)])
-        res[name] = d
+    for rep in reps.split(","):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        ik = hdr.index("Kernel Name")
+        seen = set()
+        for r in rows[2:]:
+            name = short(r[ik])
+            if name in seen:
+                continue
+            seen.add(name)
+            d = {}
+            for k in KEYS:
+                if k in hdr:
+                    d[k] = (r[hdr.index(k)], units[hdr.index(k)])
+            res[name] = d
+    for name in drop:
+        res.pop(name, None)
     for name, d in res.items():
         out_md.write(f"\n### `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
         for k, (v, u) in d.items():
@@ -86,13 +92,14 @@ def to_bytes(v, u):
 
 def main():
     tag, lcsv, rep, workload, ppl = sys.argv[1:6]
+    drop = sys.argv[6].split(",") if len(sys.argv) > 6 else ()
     with open(f"profiles/{tag}_launches.md", "w") as f:
         f.write(f"# {tag}: launch list of one timed bench.py step ({workload})\n\n"
                 "`ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu`\n\n")
         launches(lcsv, f)
     with open(f"profiles/{tag}_ncu_full.md", "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of the main kernels ({workload})\n")
-        res = full(rep, f)
+        res = full(rep, f, drop)
     tr = {}
     for name, d in res.items():
         if "dram__bytes_read.sum" in d and "nan" not in d["dram__bytes_read.sum"][0]:
