@@ -196,7 +196,9 @@ int mh_trace_from_scalp(void* stream, const void* volume, int32_t gx, int32_t gy
                         float* points_out, int32_t* length);
 /* Ordered acceptance (GenerateGuideStrandFromScalp / randomlyGenerateSegments flag logic, HairGrow.py:235-260,
  * 280-293): strands in order; reject when flag[seed voxel] >= 3, else accept and bump flag once per unique voxel
- * (mode 0: += 1; mode 1: = 1 and no gating, the scalp pass).  flag float32 [gz][gy][gx].  accepted uint8 [n]. */
+ * (mode 0: += 1; mode 1: = 1 and no gating, the scalp pass).  flag float32 [gz][gy][gx].  accepted uint8 [n].
+ * Same result as the sequential loop; mode 0 runs in batches of 512 strands whose mutual dependencies (a strand
+ * running through a later strand's seed voxel) are resolved in shared memory, mode 1 is order-free. */
 int mh_accept_strands(void* stream, const float* points, const int64_t* offsets, const int32_t* lengths,
                       const float* seeds, int64_t n, int32_t gx, int32_t gy, int32_t gz, int32_t mode,
                       float* flag, uint8_t* accepted);

@@ -126,33 +126,146 @@ __global__ void trace_scalp_kernel(Vol g, const float* __restrict__ roots, const
 // Ordered acceptance: a single warp walks the strands in order (the reference's sequential flag logic).
 // mode 0: gate on flag[seed voxel] >= 3, then flag[voxels] += 1 once per unique voxel (gather-all then scatter-all,
 //         which is what `flag[idx] += 1` does with duplicate indices);  mode 1: no gate, flag[voxels] = 1.
-__global__ void accept_kernel(const float* __restrict__ pts, const int64_t* __restrict__ offsets,
-                              const int* __restrict__ lengths, const float* __restrict__ seeds, int64_t n,
-                              int gx, int gy, int gz, int mode, float* __restrict__ flag, uint8_t* __restrict__ accepted) {
-    const int lane = threadIdx.x;
+// ---- acceptance pass (GenerateGuideStrandFromScalp / randomlyGenerateSegments flag logic, HairGrow.py:235-260, 280-293)
+// Reference: strands in seed order; strand i is kept iff it exists (>= 5 points) and flag[seed voxel_i] < 3 at that
+// moment; a kept strand bumps flag once per unique voxel it visits.  The decision of i therefore depends on the kept
+// strands j < i that run through i's seed voxel.
+//
+// mode 1 (scalp roots): no gate, flag = 1 on visited voxels -> order-free, fully parallel (accept_all_kernel).
+// mode 0: batches of AB consecutive strands, exact within and across batches (accept_batch_kernel, one CTA):
+//   1. base_i = flag[seed voxel_i] as left by the previous batches; candidates = existing strands with base_i < 3;
+//      their seed voxels go into a shared-memory hash;
+//   2. every candidate j probes the hash with the voxels it visits: a hit on the seed voxel of a LATER candidate i
+//      sets bit j of dep_i (AB-bit rows in shared memory);
+//   3. candidates with an empty dep row are kept outright; the others are resolved in index order by one warp:
+//      kept_i = base_i + popc(dep_i & kept) < 3  (dep_i only holds earlier strands, whose fate is known by then);
+//   4. kept strands add 1 to flag at each unique voxel they visit (first occurrence within the strand, atomics).
+// This is the sequential loop's result bit for bit; the sequential part shrinks to step 3 (a few shared-memory
+// words per contested strand).
+constexpr int AB = 512, AB_WORDS = AB / 32, AHT = 2048, A_THREADS = 1024, A_MAXLEN = 520;
+
+__global__ void accept_all_kernel(const float* __restrict__ pts, const int64_t* __restrict__ offsets,
+                                  const int* __restrict__ lengths, int64_t n, int gx, int gy, int gz,
+                                  float* __restrict__ flag, uint8_t* __restrict__ accepted) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
     Vol g; g.v = nullptr; g.gx = gx; g.gy = gy; g.gz = gz;
-    for (int64_t i = 0; i < n; ++i) {
-        const int len = lengths[i];
-        bool acc = len > 0;
-        if (acc && mode == 0) {
-            const float f = flag[vox_index(g, seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2])];
-            acc = !(f >= 3.0f);
+    const int len = lengths[i];
+    if (lane == 0) accepted[i] = len > 0 ? 1 : 0;
+    const float* p = pts + 3 * offsets[i];
+    for (int k = lane; k < len; k += 32) flag[vox_index(g, p[3 * k], p[3 * k + 1], p[3 * k + 2])] = 1.0f;
+}
+
+__device__ __forceinline__ unsigned accept_hash(int v) { return ((unsigned)v * 2654435761u) >> 21; }      // 11 bits = AHT
+
+__global__ void __launch_bounds__(A_THREADS)
+accept_batch_kernel(const float* __restrict__ pts, const int64_t* __restrict__ offsets, const int* __restrict__ lengths,
+                    const float* __restrict__ seeds, int64_t n, int gx, int gy, int gz, float* flag,
+                    uint8_t* __restrict__ accepted) {
+    extern __shared__ __align__(16) unsigned char a_smem[];
+    int* hkey = reinterpret_cast<int*>(a_smem);                   // [AHT] seed voxel or -1
+    int* hhead = hkey + AHT;                                      // [AHT] first candidate with that seed voxel
+    int* snext = hhead + AHT;                                     // [AB]  chain of candidates sharing a seed voxel
+    int* slen = snext + AB;                                       // [AB]
+    float* sbase = reinterpret_cast<float*>(slen + AB);           // [AB]  flag at the seed voxel when the batch starts
+    unsigned* dep = reinterpret_cast<unsigned*>(sbase + AB);      // [AB][AB_WORDS]
+    unsigned* keptm = dep + AB * AB_WORDS;                        // [AB_WORDS] kept strands of the batch
+    unsigned* contm = keptm + AB_WORDS;                           // [AB_WORDS] contested candidates (non-empty dep row)
+    int* vbuf = reinterpret_cast<int*>(contm + AB_WORDS);         // [32][A_MAXLEN] voxel ids of the strand a warp works on
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Vol g; g.v = nullptr; g.gx = gx; g.gy = gy; g.gz = gz;
+    for (int64_t b0 = 0; b0 < n; b0 += AB) {
+        const int nb = (int)min((int64_t)AB, n - b0);
+        for (int k = tid; k < AHT; k += A_THREADS) { hkey[k] = -1; hhead[k] = -1; }
+        for (int k = tid; k < AB * AB_WORDS; k += A_THREADS) dep[k] = 0u;
+        if (tid < AB_WORDS) { keptm[tid] = 0u; contm[tid] = 0u; }
+        __syncthreads();
+        // 1. candidates and their seed voxels
+        bool cand = false;
+        if (tid < nb) {
+            const int64_t i = b0 + tid;
+            const int len = lengths[i];
+            const int sv = vox_index(g, seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+            const float base = __ldcg(flag + sv);                  // L2: earlier batches updated it with atomics
+            slen[tid] = len;
+            sbase[tid] = base;
+            cand = len > 0 && !(base >= 3.0f);
+            if (cand) {
+                unsigned h = accept_hash(sv);
+                for (;;) {
+                    const int old = atomicCAS(&hkey[h], -1, sv);
+                    if (old == -1 || old == sv) { snext[tid] = atomicExch(&hhead[h], tid); break; }
+                    h = (h + 1) & (AHT - 1);
+                }
+            }
         }
-        if (lane == 0) accepted[i] = acc ? 1 : 0;
-        if (!acc) continue;                                     // warp-uniform
-        const float* p = pts + 3 * offsets[i];
-        // len <= 2*256+1 = 513 -> at most 17 rounds of 32
-        float val[17]; int idx[17];
-        int r = 0;
-        for (int k = lane; k < len; k += 32, ++r) {
-            idx[r] = vox_index(g, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
-            val[r] = flag[idx[r]];
+        __syncthreads();
+        // 2. dependencies: candidate j runs through the seed voxel of a later candidate i
+        for (int j = warp; j < nb; j += A_THREADS / 32) {
+            const bool jc = slen[j] > 0 && !(sbase[j] >= 3.0f);
+            if (!jc) continue;                                     // warp-uniform
+            const float* p = pts + 3 * offsets[b0 + j];
+            const int len = slen[j];
+            for (int k = lane; k < len; k += 32) {
+                const int v = vox_index(g, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+                unsigned h = accept_hash(v);
+                for (;;) {
+                    const int key = hkey[h];
+                    if (key == -1) break;
+                    if (key == v) {
+                        for (int i = hhead[h]; i != -1; i = snext[i])
+                            if (i > j) atomicOr(&dep[i * AB_WORDS + (j >> 5)], 1u << (j & 31));
+                        break;
+                    }
+                    h = (h + 1) & (AHT - 1);
+                }
+            }
         }
-        __syncwarp();
-        r = 0;
-        for (int k = lane; k < len; k += 32, ++r) flag[idx[r]] = (mode == 0) ? val[r] + 1.0f : 1.0f;
-        __threadfence_block();
-        __syncwarp();
+        __syncthreads();
+        // 3. uncontested candidates are kept outright; contested ones are resolved in index order by warp 0
+        if (tid < nb && cand) {
+            unsigned any = 0u;
+#pragma unroll
+            for (int w = 0; w < AB_WORDS; ++w) any |= dep[tid * AB_WORDS + w];
+            atomicOr(any ? &contm[tid >> 5] : &keptm[tid >> 5], 1u << (tid & 31));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 0; w < AB_WORDS; ++w) {
+                unsigned word = contm[w];
+                while (word) {
+                    const int b = __ffs(word) - 1;
+                    const int i = w * 32 + b;
+                    int c = (lane < AB_WORDS) ? __popc(dep[i * AB_WORDS + lane] & keptm[lane]) : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    if (lane == 0 && sbase[i] + (float)c < 3.0f) keptm[w] |= 1u << b;
+                    __syncwarp();
+                    word &= word - 1;
+                }
+            }
+        }
+        __syncthreads();
+        // 4. results; kept strands bump the flag once per unique voxel
+        if (tid < nb) accepted[b0 + tid] = (keptm[tid >> 5] >> (tid & 31)) & 1u;
+        int* vb = vbuf + warp * A_MAXLEN;
+        for (int j = warp; j < nb; j += A_THREADS / 32) {
+            if (!((keptm[j >> 5] >> (j & 31)) & 1u)) continue;    // warp-uniform
+            const float* p = pts + 3 * offsets[b0 + j];
+            const int len = min(slen[j], A_MAXLEN);
+            for (int k = lane; k < len; k += 32) vb[k] = vox_index(g, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+            __syncwarp();
+            for (int k = lane; k < len; k += 32) {
+                const int v = vb[k];
+                bool first = true;
+                for (int k2 = k - 1; k2 >= 0; --k2) if (vb[k2] == v) { first = false; break; }
+                if (first) atomicAdd(flag + v, 1.0f);
+            }
+            __syncwarp();
+        }
+        __threadfence();
+        __syncthreads();
     }
 }
 
@@ -207,7 +320,16 @@ extern "C" int mh_accept_strands(void* stream, const float* points, const int64_
     if (n == 0) return 0;
     MH_CHECK_ARG(points && offsets && lengths && flag && accepted && (mode == 1 || seeds), "null pointer");
     MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && (mode == 0 || mode == 1), "bad arguments");
-    accept_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(points, offsets, lengths, seeds, n, gx, gy, gz, mode, flag, accepted);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 1) {
+        accept_all_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(points, offsets, lengths, n, gx, gy, gz, flag, accepted);
+    } else {
+        const size_t smem = sizeof(int) * (2 * AHT + 2 * AB) + sizeof(float) * AB + sizeof(unsigned) * (AB * AB_WORDS + 2 * AB_WORDS)
+                            + sizeof(int) * 32 * A_MAXLEN;
+        cudaError_t e = cudaFuncSetAttribute(accept_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { mh_set_error("mh_accept_strands: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 2; }
+        accept_batch_kernel<<<1, A_THREADS, smem, st>>>(points, offsets, lengths, seeds, n, gx, gy, gz, flag, accepted);
+    }
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;

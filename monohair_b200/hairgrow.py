@@ -95,11 +95,21 @@ class HairGrowing:
         return acc.bool()
 
     @staticmethod
-    def _split(pts, offsets, lengths, keep):
-        idx = torch.nonzero(keep, as_tuple=False)[:, 0].cpu().numpy()
-        off = offsets.cpu().numpy()
-        ln = lengths.cpu().numpy()
-        return [pts[off[i]:off[i] + ln[i]] for i in idx]
+    def _split(pts, offsets, lengths, keep, stride=None):
+        """Kept strands as a list of [L,3] tensors (what the reference's loops build with strands.append): the kept
+        points are compacted on the device and cut by ONE torch.split, instead of one Python slice per strand.
+        `stride`: points of strand i start at i*stride (scalp batch); None: strands are packed back to back."""
+        ln = torch.where(keep, lengths, torch.zeros_like(lengths))
+        n = lengths.numel()
+        if stride is None:
+            total = int(lengths.sum().item())
+            sel = torch.repeat_interleave(keep, lengths.long(), output_size=total)
+            compact = pts[:total][sel]
+        else:
+            m = torch.arange(stride, device=pts.device)[None, :] < ln[:, None]
+            compact = pts.view(n, stride, 3)[m]
+        sizes = ln[keep].cpu().tolist()
+        return list(torch.split(compact, sizes)) if sizes else []
 
     def _scalp_batch(self, roots, normals, thrDot):
         n = roots.size(0)
@@ -141,7 +151,7 @@ class HairGrowing:
         flag = torch.zeros((self.gz, self.gy, self.gx), dtype=torch.float32, device=dev)
         pts, off, ln = self._scalp_batch(roots, normals, thrDot)
         keep = self._accept(pts, off, ln, None, flag, 1)
-        strands = self._split(pts, off, ln, keep)
+        strands = self._split(pts, off, ln, keep, stride=MAX_STEPS + 1)
         print('num guide:', len(strands))
         num_root = len(strands)
         seeds = self._positive_seeds()

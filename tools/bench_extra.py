@@ -94,6 +94,12 @@ def bench_hairgrow():
     # trace-only timing (count + write passes over all occupied voxels)
     seeds = hg._positive_seeds() + 0.6
     ms_trace = ev_time(lambda: hg._trace_batch(seeds, 0.85), reps=3, warm=1)
+    # ordered acceptance of one pass over all occupied voxels (flag volume as the scalp pass leaves it)
+    pts_a, off_a, ln_a = hg._trace_batch(seeds, 0.85)
+    flag0 = torch.zeros((hg.gz, hg.gy, hg.gx), dtype=torch.float32, device="cuda:0")
+    rp, ro, rl = hg._scalp_batch(roots, normals, 0.85)
+    hg._accept(rp, ro, rl, None, flag0, 1)
+    ms_accept = ev_time(lambda: hg._accept(pts_a, off_a, ln_a, seeds, flag0.clone(), 0), reps=3, warm=1)
     # CPU oracle on a bounded sample
     volc = H.Volume(vol[..., 3].cpu().numpy(), vol[..., :3].permute(3, 0, 1, 2).contiguous().cpu().numpy())
     sd = seeds.cpu().numpy()[:: max(1, M // 300)][:300].copy()
@@ -106,6 +112,7 @@ def bench_hairgrow():
                       "occupied_voxels": M, "seeds": int(60000 + 2 * M), "strands": len(strands), "num_root": num_root,
                       "points": n_pts, "b200_s_total": dt, "strands_per_s": len(strands) / dt,
                       "trace_only_ms_per_pass": ms_trace, "trace_seeds_per_s": M / (ms_trace * 1e-3),
+                      "accept_ms_per_pass": ms_accept,
                       "cpu_oracle_seeds_per_s": sd.shape[0] / cpu, "cpu_sample": f"{sd.shape[0]} seeds, 1 core (scalar port)"}))
 
 
