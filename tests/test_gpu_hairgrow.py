@@ -88,3 +88,55 @@ def test_full_size_properties():
     s = pts[int(off[i]):int(off[i]) + int(ln[i])]
     step = (s[1:] - s[:-1]).norm(dim=1)
     assert torch.allclose(step, torch.ones_like(step), atol=1e-4)
+
+
+def test_accept_strands_dense_conflicts_vs_sequential_loop():
+    """mh_accept_strands (batched, parallel) against the reference's sequential flag loop (HairGrow.py:246-260) written
+    out in numpy, on a tiny grid where nearly every strand crosses other strands' seed voxels: several strands per
+    seed voxel, strands revisiting a voxel, missing strands, three batches of 512 and a ragged tail, both modes."""
+    import ctypes as C
+    from monohair_b200._lib import check, lib, ptr, stream_ptr
+    rng = np.random.default_rng(7)
+    gx, gy, gz = 11, 9, 13
+    n = 3 * 512 + 77
+    lengths = np.where(rng.random(n) < 0.25, 0, rng.integers(5, 70, n)).astype(np.int32)
+    offsets = (np.cumsum(lengths) - lengths).astype(np.int64)
+    pts = np.zeros((max(int(lengths.sum()), 1), 3), np.float32)
+    for i in range(n):
+        p = rng.uniform(-0.5, [gx + 0.5, gy + 0.5, gz + 0.5])
+        for k in range(lengths[i]):
+            pts[offsets[i] + k] = p
+            p = p + rng.normal(0, 0.7, 3)                              # short steps: voxels repeat and get revisited
+    seeds = rng.uniform(-0.5, [gx + 0.5, gy + 0.5, gz + 0.5], (n, 3)).astype(np.float32)
+    m = min(len(seeds[::7]), len(seeds[3::7]))
+    seeds[::7][:m] = seeds[3::7][:m]                                   # shared seed voxels
+
+    def vox(q):
+        ix = np.clip(q[..., 0].astype(np.int64), 0, gx - 1)           # .type(torch.long): truncation, then clamp
+        iy = np.clip(q[..., 1].astype(np.int64), 0, gy - 1)
+        iz = np.clip(q[..., 2].astype(np.int64), 0, gz - 1)
+        return (iz * gy + iy) * gx + ix
+
+    for mode in (0, 1):
+        flag0 = rng.integers(0, 3, gx * gy * gz).astype(np.float32)
+        ref_flag, ref_acc = flag0.copy(), np.zeros(n, np.uint8)
+        for i in range(n):
+            if lengths[i] == 0:
+                continue
+            if mode == 0 and ref_flag[vox(seeds[i])] >= 3:
+                continue
+            ref_acc[i] = 1
+            u = np.unique(vox(pts[offsets[i]: offsets[i] + lengths[i]]))
+            if mode == 0:
+                ref_flag[u] += 1
+            else:
+                ref_flag[u] = 1
+        dev = torch.device("cuda:0")
+        d = lambda a: torch.from_numpy(a).to(dev).contiguous()
+        t_pts, t_off, t_len, t_seeds, t_flag = d(pts), d(offsets), d(lengths), d(seeds), d(flag0.copy())
+        acc = torch.empty((n,), dtype=torch.uint8, device=dev)
+        check(lib().mh_accept_strands(stream_ptr(dev), ptr(t_pts), ptr(t_off), ptr(t_len), ptr(t_seeds), n, gx, gy, gz, mode,
+                                      ptr(t_flag), ptr(acc)), "mh_accept_strands")
+        assert np.array_equal(acc.cpu().numpy(), ref_acc), f"mode {mode}: accepted set differs"
+        assert np.array_equal(t_flag.cpu().numpy(), ref_flag), f"mode {mode}: flag volume differs"
+        assert 0 < ref_acc.sum() < (lengths > 0).sum() or mode == 1
