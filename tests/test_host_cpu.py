@@ -60,3 +60,28 @@ def test_sample_offsets_match_oracle():
     from oracle import pmvo_oracle as O
     assert torch.equal(PMVO._sample_offsets(90), O.sample_offsets(90))
     assert PMVO._sample_offsets(90).numel() == 90
+
+
+def test_strand_split_matches_per_strand_slicing():
+    """HairGrowing._split (device-side compaction + one torch.split) == slicing strand by strand, for the packed layout
+    of the segment passes and the fixed-stride layout of the scalp pass; runs on CPU tensors."""
+    from monohair_b200.hairgrow import HairGrowing
+    g = torch.Generator().manual_seed(3)
+    n = 57
+    lengths = torch.where(torch.rand(n, generator=g) < 0.3, torch.zeros(n, dtype=torch.int32),
+                          torch.randint(5, 40, (n,), generator=g, dtype=torch.int32))
+    keep = (torch.rand(n, generator=g) < 0.6) & (lengths > 0)
+    # packed: strands back to back
+    offsets = torch.cumsum(lengths.long(), 0) - lengths.long()
+    pts = torch.rand((int(lengths.sum()), 3), generator=g)
+    got = HairGrowing._split(pts, offsets, lengths, keep)
+    want = [pts[offsets[i]: offsets[i] + lengths[i]] for i in range(n) if keep[i]]
+    assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
+    # fixed stride: strand i starts at i * stride
+    stride = 41
+    pts2 = torch.rand((n * stride, 3), generator=g)
+    off2 = torch.arange(n, dtype=torch.int64) * stride
+    got = HairGrowing._split(pts2, off2, lengths, keep, stride=stride)
+    want = [pts2[off2[i]: off2[i] + lengths[i]] for i in range(n) if keep[i]]
+    assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
+    assert HairGrowing._split(pts, offsets, lengths, torch.zeros(n, dtype=torch.bool)) == []
