@@ -1,5 +1,6 @@
 """Drop-in entry point: `python HairGrow.py --yaml=configs/reconstruct/<case>` -- the generate_segments phase of the
-reference's HairGrow.py (:876-919) on monohair_b200's trace kernels; writes scalp_segment.hair and num_root.npy.
+reference's HairGrow.py (:876-919) on monohair_b200's trace kernels; writes scalp_segment.hair,
+scalp_segment_smooth.hair and num_root.npy.
 The connect / smooth phases (HairGrow.py:925-976) are "next" rows of SURVEY.md §8f and are not part of this path."""
 import os
 import sys
@@ -8,7 +9,7 @@ import numpy as np
 import torch
 
 from monohair_b200 import options
-from monohair_b200.hairgrow import HairGrowing, points_to_voxel, save_hair_strands, voxel_to_points  # noqa: F401
+from monohair_b200.hairgrow import HairGrowing, points_to_voxel, save_hair_strands, smooth_strands, voxel_to_points  # noqa: F401
 from monohair_b200.pmvo_utils import read_obj, sample_points_uniformly
 
 
@@ -49,6 +50,8 @@ def main():
         strands, num_root = solver.GenerateGuideStrandFromScalp(scalp_points, scalp_normals, None, args.HairGenerate.grow_threshold)
         strands = solver.VoxelToWorld(strands, args.bust_to_origin)
         save_hair_strands(os.path.join(args.save_path, 'scalp_segment.hair'), strands)
+        strands = smooth_strands(strands, 4.0, 2.0, device=args.device)                       # HairGrow.py:914-916
+        save_hair_strands(os.path.join(args.save_path, 'scalp_segment_smooth.hair'), strands)
         np.save(args.save_path + '/num_root.npy', np.array(num_root))
     if args.HairGenerate.connect_segments or args.HairGenerate.connect_scalp:
         print('connect_segments / connect_scalp are outside the B200 hot path (SURVEY.md §8f); '

@@ -203,6 +203,15 @@ int mh_accept_strands(void* stream, const float* points, const int64_t* offsets,
                       const float* seeds, int64_t n, int32_t gx, int32_t gy, int32_t gz, int32_t mode,
                       float* flag, uint8_t* accepted);
 
+/* ---- strand smoothing (Utils/Utils.py:1148-1198 smnooth_strand / smooth_strands; HairGrow.py:914, :950, :975) ---- */
+/* Per strand (points[offsets[i] .. +lengths[i])) and axis: least squares of [lap*L ; pos*I] x = [0 ; pos*s] with L the
+ * second-difference operator (first differences at the ends), solved in float64 through the pentadiagonal normal
+ * equations, rounded to float32 like the reference's in-place store.  Strands of fewer than 2 points are copied. */
+int64_t mh_smooth_strands_workspace_bytes(int64_t total_points);
+int mh_smooth_strands(void* stream, const float* points /*[T][3]*/, const int64_t* offsets /*[n]*/,
+                      const int32_t* lengths /*[n]*/, int64_t n_strands, double lap_constraint, double pos_constraint,
+                      float* points_out /*[T][3]*/, void* workspace, int64_t workspace_bytes, int64_t total_points);
+
 /* ---- Gabor bank (GaborFilter.py:29-145, calc_orientation_maps.py:18-49) ------------------------------- */
 /* calOrientationGabor.filter+forward for iter=1: image [H][W] -> orient [H][W] (radians), conf [H][W],
 int64_t mh_gabor_workspace_bytes(int32_t H, int32_t W, int32_t n_filters);

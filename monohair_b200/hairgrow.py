@@ -218,6 +218,37 @@ class HairGrowing:
         return out
 
 
+def smooth_strands(strands, lap_constraint=2.0, pos_constraint=1.0, fix_tips=False, device="cuda:0"):
+    """Utils/Utils.py:1194-1198 (smnooth_strand :1148-1192 per strand) on the device: list of [L,3] arrays (or tensors)
+    -> list of smoothed [L,3] float32 numpy arrays (the reference stores the float64 solution back into the strand's
+    float32 array).  With fix_tips the end points keep their positions (:1186-1187)."""
+    if len(strands) == 0:
+        return strands
+    dev = torch.device(device)
+    arrs = [np.asarray(s.detach().cpu() if torch.is_tensor(s) else s, dtype=np.float32).reshape(-1, 3) for s in strands]
+    lengths = np.array([a.shape[0] for a in arrs], dtype=np.int32)
+    offsets = (np.cumsum(lengths.astype(np.int64)) - lengths).astype(np.int64)
+    total = int(lengths.sum())
+    pts = torch.from_numpy(np.ascontiguousarray(np.concatenate(arrs, 0))).to(dev)
+    out = torch.empty_like(pts)
+    wsb = lib().mh_smooth_strands_workspace_bytes(total)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    t_off, t_len = torch.from_numpy(offsets).to(dev), torch.from_numpy(lengths).to(dev)
+    with torch.cuda.device(dev):
+        check(lib().mh_smooth_strands(stream_ptr(dev), ptr(pts), ptr(t_off), ptr(t_len), len(arrs), float(lap_constraint),
+                                      float(pos_constraint), ptr(out), ptr(ws), wsb, total), "mh_smooth_strands")
+    res = out.cpu().numpy()
+    smoothed = []
+    for a, o, n in zip(arrs, offsets, lengths):
+        sm = res[o:o + n].copy()
+        if fix_tips and n >= 2:
+            tips = a.copy()
+            tips[1:-1] = sm[1:-1]
+            sm = tips
+        smoothed.append(sm)
+    return smoothed
+
+
 def save_hair_strands(path, strands):
     """Utils/Utils.py:1246-1262: uint32 n_strands, uint32 n_points, uint16[n_strands], float32[n_points*3]."""
     segments = np.array([s.shape[0] for s in strands], dtype=np.uint16)

@@ -177,3 +177,70 @@ def segments_passes(vol, seeds, flag, thr, jitter, passes):
 def randomly_generate_segments(vol, thr, jitter, passes=3):
     """randomlyGenerateSegments (HairGrow.py:269-299)."""
     return segments_passes(vol, positive_seeds(vol), np.zeros_like(vol.occ), thr, jitter, passes)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Strand smoothing (Utils/Utils.py:1148-1198).  TEST INFRASTRUCTURE like the rest of this file.
+def smooth_strand(strand, lap_constraint=2.0, pos_constraint=1.0, fix_tips=False):
+    """smnooth_strand (Utils.py:1148-1192): least squares of [lap*L ; pos*I] x = [0 ; pos*s] per axis through the normal
+    equations, solved with scipy's sparse LU in float64 and stored back into an array of the strand's dtype.
+    L: rows (1,-1), (-1,2,-1) x (n-2), (-1,1)."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import spsolve
+    n = strand.shape[0]
+    rows, cols, vals = [0, 0], [0, 1], [1.0, -1.0]
+    for k in range(1, n - 1):
+        rows += [k, k, k]; cols += [k - 1, k, k + 1]; vals += [-1.0, 2.0, -1.0]
+    rows += [n - 1, n - 1]; cols += [n - 2, n - 1]; vals += [-1.0, 1.0]
+    vals = [v * lap_constraint for v in vals]
+    rows += list(range(n, 2 * n)); cols += list(range(n)); vals += [pos_constraint] * n
+    A = sp.coo_matrix((np.array(vals), (np.array(rows), np.array(cols))), shape=(2 * n, n))
+    At = A.transpose()
+    AtA = At.dot(A)
+    out = np.copy(strand)
+    for a in range(3):
+        b = np.zeros(2 * n)
+        b[n:] = out[:, a] * pos_constraint                 # float32 strand: the product is rounded to float32 (Utils.py:1179)
+        out[:, a] = spsolve(AtA, At.dot(b))[:n]
+    if fix_tips:
+        res = strand.copy()
+        res[1:-1] = out[1:-1]
+        return res
+    return out
+
+
+def smooth_strand_banded(strand, lap_constraint=2.0, pos_constraint=1.0):
+    """The same system solved the way csrc/smooth.cu does (bands of A^T A by accumulated row outer products, banded
+    Cholesky, float64): used on CPU to check that formulation against smooth_strand before it is trusted on the GPU."""
+    s = np.asarray(strand)
+    n = s.shape[0]
+    l2, p2 = float(lap_constraint) ** 2, float(pos_constraint) ** 2
+    D, E, F = np.full(n, p2), np.zeros(n), np.zeros(n)
+    D[0] += l2; D[1] += l2; E[0] += -l2
+    for k in range(1, n - 1):
+        D[k - 1] += l2; D[k] += 4 * l2; D[k + 1] += l2
+        E[k - 1] += -2 * l2; E[k] += -2 * l2; F[k - 1] += l2
+    D[n - 2] += l2; D[n - 1] += l2; E[n - 2] += -l2
+    for j in range(n):
+        t = D[j]
+        if j >= 1: t -= E[j - 1] ** 2
+        if j >= 2: t -= F[j - 2] ** 2
+        D[j] = np.sqrt(t)
+        if j + 1 < n:
+            u = E[j]
+            if j >= 1: u -= F[j - 1] * E[j - 1]
+            E[j] = u / D[j]
+        if j + 2 < n: F[j] = F[j] / D[j]
+    X = np.zeros((n, 3))
+    rhs = float(pos_constraint) * (s.astype(np.float32) * np.float32(pos_constraint)).astype(np.float64)
+    for j in range(n):
+        y = rhs[j].copy()
+        if j >= 1: y -= E[j - 1] * X[j - 1]
+        if j >= 2: y -= F[j - 2] * X[j - 2]
+        X[j] = y / D[j]
+    for j in range(n - 1, -1, -1):
+        x = X[j].copy()
+        if j + 1 < n: x -= E[j] * X[j + 1]
+        if j + 2 < n: x -= F[j] * X[j + 2]
+        X[j] = x / D[j]
+    return X.astype(s.dtype)

@@ -140,3 +140,24 @@ def test_accept_strands_dense_conflicts_vs_sequential_loop():
         assert np.array_equal(acc.cpu().numpy(), ref_acc), f"mode {mode}: accepted set differs"
         assert np.array_equal(t_flag.cpu().numpy(), ref_flag), f"mode {mode}: flag volume differs"
         assert 0 < ref_acc.sum() < (lengths > 0).sum() or mode == 1
+
+
+def test_smooth_strands_vs_reference_golden():
+    """mh_smooth_strands (float64 banded Cholesky per strand, rounded to float32) against the unmodified reference's
+    smooth_strands (scipy sparse LU in float64, stored as float32): equal up to one float32 ulp -- the two float64
+    solvers differ in the last bits -- and bit-identical for > 99.9 % of the values.  fix_tips keeps the end points."""
+    from monohair_b200.hairgrow import smooth_strands
+    g = load("smooth_small")
+    lens = g["lengths"]
+    offs = np.cumsum(lens) - lens
+    ins = [g["pts"][o:o + n] for o, n in zip(offs, lens)]
+    for key, lap, pos, fix in (("out_4_2", 4.0, 2.0, False), ("out_2_1_fix", 2.0, 1.0, True)):
+        got = np.concatenate(smooth_strands([s.copy() for s in ins], lap, pos, fix), 0)
+        want = g[key]
+        assert got.dtype == np.float32 and got.shape == want.shape
+        ulp = np.spacing(np.abs(want).astype(np.float32))
+        assert np.all(np.abs(got - want) <= ulp), f"{key}: max diff {np.abs(got - want).max()}"
+        same = np.mean(got == want)
+        print(f"smooth {key}: {same * 100:.3f}% of {want.size} values bit-identical")
+        assert same > 0.999
+    assert smooth_strands([], 4.0, 2.0) == []

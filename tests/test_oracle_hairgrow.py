@@ -28,3 +28,20 @@ def test_random_segments_bit_exact():
     strands = H.randomly_generate_segments(vol, float(g["thr"]), g["jitter"], passes=3)
     assert np.array_equal(np.array([s.shape[0] for s in strands], np.int32), g["segments_len"])
     assert np.array_equal(np.concatenate(strands), g["segments_pts"])
+
+
+def test_smooth_strands_oracle_vs_reference_golden():
+    """oracle smooth_strand (scipy sparse LU, as the reference) == the unmodified reference bit for bit; the banded-Cholesky
+    formulation the CUDA kernel uses agrees with it on the stored float32 values."""
+    g = load("smooth_small")
+    ins = _split(g["pts"], g["lengths"])
+    for key, lap, pos, fix in (("out_4_2", 4.0, 2.0, False), ("out_2_1_fix", 2.0, 1.0, True)):
+        want = _split(g[key], g["lengths"])
+        for s, w in zip(ins, want):
+            got = H.smooth_strand(s.copy(), lap, pos, fix)
+            assert got.dtype == np.float32 and np.array_equal(got, w)
+            if not fix:
+                banded = H.smooth_strand_banded(s.copy(), lap, pos)
+                ulp = np.spacing(np.abs(w).astype(np.float32))
+                assert np.all(np.abs(banded - w) <= ulp)
+                assert np.mean(banded == w) > 0.999
