@@ -414,6 +414,22 @@ def voxel_fuse(select_points, select_ori, grid=(256, 256, 192), voxel_min=(-0.32
     return occ, ori
 
 
+def merge_inner(vm, occ, ori, raw, grid=(256, 256, 192), voxel_min=(-0.32, -0.32, -0.24), voxel_size=0.005 / 2):
+    """PMVO.refine, infer_inner branch (PMVO.py:733-751): the points of DeepMVSHair's raw.npy ([M,7] = xyz, ori, occ)
+    that no view sees overwrite the fused volume; orientations flipped to y <= 0; numpy advanced-index assignment, so
+    among several points of one voxel the LAST one wins.  occ/ori are modified in place.
+    -> (un_visible_points [m,3] float32, unvisible_ori [m,3] float32) = what the reference saves as coarse*.npy."""
+    points = raw[:, :3].astype(np.float32)
+    c_ori = raw[:, 3:6].astype(np.float32)
+    c_ori[c_ori[:, 1] > 0] *= -1
+    unv = compute_unvisible_points(vm, torch.from_numpy(points)).numpy()
+    up, uo = points[unv], c_ori[unv]
+    x, y, z = p2v(up.copy(), np.array(voxel_min), voxel_size, np.array(grid).astype(np.int32))
+    occ[x, y, z] = 1
+    ori[x, y, z] = uo
+    return up, uo
+
+
 def mat_layout(occ, ori):
     """PMVO.py:753-756: in-memory [X,Y,Z(,3)] -> arrays saved as Occ3D.mat / Ori3D.mat."""
     g = occ.shape

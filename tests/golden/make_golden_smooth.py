@@ -1,6 +1,5 @@
 """Golden vectors for strand smoothing from the UNMODIFIED reference (Utils/Utils.py smooth_strands, :1148-1198).
     python tests/golden/make_golden_smooth.py      (build container only: needs /root/reference)"""
-import importlib
 import os
 import sys
 
@@ -22,9 +21,7 @@ def strands(seed=0):
 
 
 def main():
-    ref_import.install_stubs()
-    sys.path.insert(0, ref_import.REF_ROOT)
-    U = importlib.import_module("Utils.Utils")
+    U = ref_import.import_reference()["Utils"]
     s = strands()
     a = U.smooth_strands([x.copy() for x in s], 4.0, 2.0)                  # HairGrow.py:914 parameters
     b = U.smooth_strands([x.copy() for x in s], 2.0, 1.0, True)            # defaults + fix_tips

@@ -47,18 +47,45 @@ def install_stubs():
         sk.filters = _stub("skimage.filters", difference_of_gaussians=None, gabor_kernel=None)
 
 
+def _pin_reference_packages():
+    """The reference's `Utils` directory has no __init__.py (a namespace package), this repository's drop-in `Utils`
+    does -- and a regular package beats a namespace package wherever it sits on sys.path.  Bind the name `Utils` (and
+    the top-level module names both trees use) to the REFERENCE explicitly, and refuse to go on if anything that is
+    already imported under those names comes from elsewhere."""
+    for name in ("Utils", "PMVO", "HairGrow", "options", "log"):
+        m = sys.modules.get(name)
+        origin = getattr(m, "__file__", None) or (list(getattr(m, "__path__", [])) or [""])[0]
+        if m is not None and not str(origin).startswith(REF_ROOT):
+            for k in [k for k in sys.modules if k == name or k.startswith(name + ".")]:
+                del sys.modules[k]
+    pkg = types.ModuleType("Utils")
+    pkg.__path__ = [REF_ROOT + "/Utils"]
+    pkg.__package__ = "Utils"
+    sys.modules.setdefault("Utils", pkg)
+
+
+def _assert_from_reference(mods):
+    for name, m in list(mods.items()) + [(k, v) for k, v in sys.modules.items() if k.startswith("Utils.")]:
+        f = getattr(m, "__file__", None)
+        assert f is None or f.startswith(REF_ROOT), f"{name} was imported from {f}, not from the reference"
+
+
 def import_reference():
-    """returns dict of reference modules (PMVO, HairGrow, Camera_utils, PMVO_utils, GaborFilter)."""
+    """returns dict of reference modules (PMVO, HairGrow, Camera_utils, PMVO_utils, Utils)."""
     install_stubs()
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
-        sys.path.insert(0, REF_ROOT + "/preprocess_capture_data")
+    for q in (REF_ROOT + "/preprocess_capture_data", REF_ROOT):
+        if q in sys.path:
+            sys.path.remove(q)
+        sys.path.insert(0, q)
+    _pin_reference_packages()
     import importlib
     mods = {}
     mods["PMVO"] = importlib.import_module("PMVO")
     mods["HairGrow"] = importlib.import_module("HairGrow")
     mods["Camera_utils"] = importlib.import_module("Utils.Camera_utils")
     mods["PMVO_utils"] = importlib.import_module("Utils.PMVO_utils")
+    mods["Utils"] = importlib.import_module("Utils.Utils")
+    _assert_from_reference(mods)
     return mods
 
 

@@ -56,3 +56,26 @@ def test_refine_and_voxelise_bit_exact(case):
     vals = np.stack([mori[i, j, [k, k + Z, k + 2 * Z]] for i, j, k in nz])
     assert np.array_equal(vals, g["mat_ori_nz"])
     assert tuple(mori.shape) == tuple(g["mat_ori_shape"])
+
+
+def test_inner_merge_bit_exact():
+    """infer_inner re-entry (PMVO.py:874-880): re-voxelise the stored refine results, then overwrite with the invisible
+    points of raw.npy -- oracle vs the unmodified reference's full/Occ3D.mat, Ori3D.mat, coarse*.npy."""
+    g = load("pmvo_p7")
+    gi = load("pmvo_p7_inner")
+    vm = O.ViewMaps.from_scene(scene_of(g))
+    scalp = g["scalp"]
+    tree, smax = KDTree(data=scalp), scalp.max(0)
+    p, o, l = g["fwd_points"].astype(np.float32), g["ref_select_o"], g["ref_min_loss"]
+    idx = np.where(l < float(g["thr"]))[0]
+    fp, fo = O.unvisible_orientation(vm, p[idx], o[idx], g["filter_unvisible_in"], 1, tree, smax)
+    occ, ori = O.voxel_fuse(np.concatenate([p[idx], fp]), np.concatenate([o[idx], fo]))
+    up, uo = O.merge_inner(vm, occ, ori, gi["raw"])
+    assert np.array_equal(up, gi["coarse"]) and np.array_equal(uo, gi["coarse_ori"])
+    assert 0 < up.shape[0] < gi["raw"].shape[0]
+    mo, mori = O.mat_layout(occ, ori)
+    nz = np.argwhere(mo > 0)
+    assert np.array_equal(nz, gi["mat_occ_nz"]) and len(nz) > len(g["mat_occ_nz"])
+    Z = mo.shape[2]
+    vals = np.stack([mori[i, j, [k, k + Z, k + 2 * Z]] for i, j, k in nz])
+    assert np.array_equal(vals, gi["mat_ori_nz"])
