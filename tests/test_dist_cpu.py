@@ -1,5 +1,6 @@
 """CPU, world_size 2 over gloo: the host-side sharding logic of the multi-GPU path (monohair_b200/pipeline.py):
-contiguous shards, padded all-gather of per-point results, and the volume all-reduce with disjoint z-slabs."""
+contiguous shards, padded all-gather of per-point results, the volume all-reduce with disjoint z-slabs, and the stage
+wrappers (forward / filter / head filter / kNN / fusion with a validity mask) against their single-rank results."""
 import os
 import socket
 
@@ -45,6 +46,64 @@ def _worker(rank, world, port, q):
     mine[za:zb] = vol_full[za:zb]
     dist.all_reduce(mine, op=dist.ReduceOp.SUM)
     assert torch.equal(mine, vol_full)              # disjoint support: bit-exact
+    # 4) the stage wrappers themselves, with CPU stand-ins for the kernels (per-point / per-voxel independent functions):
+    #    sharded over the two ranks they must return exactly what the single-rank path returns
+    from monohair_b200 import pmvo as P
+
+    class FakePM:
+        device = torch.device("cpu")
+        visible_threshold = 1
+
+        def forward(self, pts):
+            o = torch.stack([pts[:, 0] * 2, pts[:, 1] - 1, pts[:, 2] ** 2], 1)
+            return pts, o, pts.sum(1), pts[:, 0] > 0
+
+        def filter_counters(self, pts):
+            return None, torch.stack([pts[:, 0], pts[:, 1], pts[:, 2], pts.sum(1), pts.prod(1)], 0)
+
+        def filter_decide(self, cnt):
+            return cnt[3] > 0, cnt[4] > 0
+
+        def filter_head_points(self, pts, thr):
+            return pts[:, 1] > 0.3
+
+        def refine_loss_raw(self, pts, center):
+            return (pts * center).sum(1)
+
+    def cpu_knn(ref, query, k, dev):
+        d = torch.cdist(query.double(), ref.double())
+        return d.topk(k, dim=1, largest=False).indices.int()
+
+    def cpu_fuse(pts, dirs, dev, grid, voxel_min, voxel_size, return_index=False, valid=None):
+        gx, gy, gz = [int(v) for v in grid]
+        vol = torch.zeros((gz, gy, gx, 4))
+        z = torch.round((-(pts[:, 2].double()) - float(voxel_min[2])) / float(voxel_size)).clamp_(0, gz - 1).long()
+        keep = torch.ones(pts.size(0), dtype=torch.bool) if valid is None else valid.bool()
+        for i in torch.nonzero(keep)[:, 0].tolist():                 # "last point of a slab wins": any per-voxel rule will do
+            vol[z[i], 0, 0] = torch.cat([dirs[i], torch.ones(1)])
+        return vol
+    P.knn, P.voxel_fuse = cpu_knn, cpu_fuse
+    pm = FakePM()
+    g = torch.Generator().manual_seed(5)
+    pts = torch.rand((1003, 3), generator=g) - 0.4
+    dirs = torch.rand((1003, 3), generator=g)
+    valid = torch.rand(1003, generator=g) < 0.7
+    grid, vmin, vs = (2, 2, 24), (-0.32, -0.32, -0.6), 0.05
+    multi = (PL.forward_stage(pm, pts), PL.filter_stage(pm, pts), PL.head_filter_stage(pm, pts, 1),
+             PL.knn_stage(pts[:200], pts, 7, pm.device), PL.fuse_stage(pm, pts, dirs, grid, vmin, vs, valid=valid),
+             PL.fuse_stage(pm, pts, dirs, grid, vmin, vs))
+    PL._FORCE_SINGLE = True
+    single = (PL.forward_stage(pm, pts), PL.filter_stage(pm, pts), PL.head_filter_stage(pm, pts, 1),
+              PL.knn_stage(pts[:200], pts, 7, pm.device), PL.fuse_stage(pm, pts, dirs, grid, vmin, vs, valid=valid),
+              PL.fuse_stage(pm, pts, dirs, grid, vmin, vs))
+    PL._FORCE_SINGLE = False
+
+    def same(a, b):
+        if isinstance(a, (tuple, list)):
+            return all(same(x, y) for x, y in zip(a, b))
+        return torch.equal(a, b)
+    for name, m, s1 in zip(("forward", "filter", "head_filter", "knn", "fuse(valid)", "fuse"), multi, single):
+        assert same(m, s1), f"{name}_stage: sharded result differs from the single-rank result"
     q.put((rank, "ok"))
     dist.destroy_process_group()
 
