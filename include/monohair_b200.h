@@ -160,11 +160,26 @@ int mh_voxel_fuse_plane_init(void* stream, void* plane, int32_t gx, int32_t gy, 
  * float64 index math (np.round half-even), takes the per-voxel medoid in original point order and writes the
  * fused volume as float4 [gz][gy][gx] = {ori.x, -ori.y, -ori.z, occ}: the layout/sign HairGrowing.__init__
  * builds from the .mat pair (HairGrow.py:45-55).  vox_index int32 [n] (linear id x*gy*gz+y*gz+z; may be NULL).
- * valid (optional): points with valid[i] == 0 are skipped, as if they had been removed from the arrays. */
+ * valid (optional): points with valid[i] == 0 are skipped, as if they had been removed from the arrays.
+ * The volume's zero fill runs on an internal auxiliary stream, concurrent with the binning kernel, and is joined back
+ * into `stream` before the medoid kernel writes its winners. */
 int mh_voxel_fuse(void* stream, const float* points, const float* dirs, const uint8_t* valid /*[n] or NULL*/, int64_t n,
                   const double* voxel_min_host /*[3]*/, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
                   void* volume /*float4 [gz][gy][gx]*/, int32_t* vox_index, void* plane, void* workspace,
                   int64_t workspace_bytes);
+/* The same fusion, stopping at the per-voxel winners: winners float4 [capacity] = {ori.x, -ori.y, -ori.z, key bits}
+ * (key = (z*gy + y)*gx + x as int32 bits; entries beyond *count carry key -1), count int32 [1] (may be NULL).
+ * capacity >= min(n, voxels).  This is the multi-GPU exchange format: ranks fuse disjoint voxel sets (via `valid`),
+ * all-gather their winner lists (16 B per occupied voxel) and scatter the union (mh_voxel_scatter) -- exactly the
+ * dense all-reduce(SUM) of disjoint volumes, without moving the zeros. */
+int mh_voxel_fuse_winners(void* stream, const float* points, const float* dirs, const uint8_t* valid, int64_t n,
+                          const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
+                          void* winners, int64_t capacity, int32_t* count, int32_t* vox_index, void* plane,
+                          void* workspace, int64_t workspace_bytes);
+/* volume[key] = {w.x, w.y, w.z, 1} for the m winners with key >= 0; zero_fill != 0 clears the volume first (TMA bulk
+ * stores from a zeroed shared-memory tile, one CTA per SM). */
+int mh_voxel_scatter(void* stream, const void* winners, int64_t m, int32_t gx, int32_t gy, int32_t gz, void* volume,
+                     int32_t zero_fill);
 /* Synchronous, informational: largest per-voxel point count seen by the last mh_voxel_fuse on this workspace if some
  * voxel held more than 32 points (the slower overflow path), else 0. */
 int mh_voxel_fuse_max_points(const void* workspace, int32_t* max_k_host);

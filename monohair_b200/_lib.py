@@ -59,6 +59,8 @@ _SIGS = {
     "mh_medoid_gather": (C.c_int, [p, p, p, i64, i32, p, p]),
     "mh_voxel_fuse_workspace_bytes": (i64, [i64, i32, i32, i32]),
     "mh_voxel_fuse": (C.c_int, [p, p, p, p, i64, p, f64, i32, i32, i32, p, p, p, p, i64]),
+    "mh_voxel_fuse_winners": (C.c_int, [p, p, p, p, i64, p, f64, i32, i32, i32, p, i64, p, p, p, p, i64]),
+    "mh_voxel_scatter": (C.c_int, [p, p, i64, i32, i32, i32, p, i32]),
     "mh_voxel_fuse_plane_bytes": (i64, [i32, i32, i32]),
     "mh_voxel_fuse_plane_init": (C.c_int, [p, p, i32, i32, i32]),
     "mh_voxel_fuse_max_points": (C.c_int, [p, p]),

@@ -1,17 +1,16 @@
 // Multi-view orientation / occupancy fusion into the voxel volume (PMVO.refine, PMVO.py:695-764).
 //
-// The reference builds a Python dict keyed by "x_y_z" and calls compute_points_similarity per voxel.  Here:
-//   1 key      p2v in float64 with round-half-even (PMVO_utils.py:386-404); per-voxel count (atomics)
-//   2 scan     exclusive scan of the dense count volume -> bucket starts
-//   3 fill     point ids into their voxel's bucket
-//   4 fuse     one thread per voxel, x-fastest: empty voxels stream zeros, occupied voxels sort their bucket
-//              back into original point order (first-index tie-break of argmax) and write the medoid.
+// The reference builds a Python dict keyed by "x_y_z" and calls compute_points_similarity per voxel.  Here (details at
+// "fusion passes" below): a zero fill of the volume on an auxiliary stream, concurrent with a binning kernel that groups
+// the points into per-voxel records through one 64-bit atomic per (warp, voxel) group on a persistent, self-cleaning
+// 8 B/voxel plane; then a medoid kernel (warp per record, lane = candidate, torch.mean's summation order) that writes the
+// winners straight into the volume -- or into a compact winner list, the multi-GPU exchange format.
 // Volume layout: float4 [gz][gy][gx] = {ori.x, -ori.y, -ori.z, occ}: the frame HairGrowing works in
-// (HairGrow.py:45-55), one 16 B fetch per trace step.  Bucket keys use the same z,y,x order so pass 4 reads
-// its 8 B of bucket bounds and writes its 16 B fully coalesced.
-// Bound: HBM streaming.  Algorithmic bytes = n*(12+12) point reads + 4 B/voxel count write+read (x2 for the
-// scan) + 16 B/voxel volume write; 256x256x192: 12.58 M voxels -> 201 MB of volume writes dominate.
+// (HairGrow.py:45-55), one 16 B fetch per trace step.
+// Bound: HBM streaming.  Algorithmic bytes = n*(12+12+4) point/direction/key + n*16 record traffic + 16 B/voxel volume
+// write; 256x256x192: 12.58 M voxels -> 201 MB of volume writes dominate.
 #include <algorithm>
+#include <cstdlib>
 #include "mh_common.cuh"
 #include "mh_torch_sum.cuh"
 
@@ -31,12 +30,6 @@ __device__ __forceinline__ void p2v(const VGrid& g, float px, float py, float pz
     z = (int)fmin(fmax(fz, 0.0), (double)(g.gz - 1));
 }
 
-// flipped direction of point i (PMVO.py:702-703: ori[ori.y>0] *= -1)
-__device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, float& a, float& b, float& c) {
-    a = dirs[3 * i]; b = dirs[3 * i + 1]; c = dirs[3 * i + 2];
-    if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
-}
-
 // ---- fusion passes ---------------------------------------------------------------------------------------
 // Shape of the problem: n points (1.7 M) fall into M occupied voxels (81 k, ~20 points each) of a 12.6 M-voxel grid
 // whose 16 B/voxel zero fill (201 MB) is the only bandwidth-sized term; grouping points by voxel is latency bound
@@ -54,7 +47,7 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int i, 
 // The plane is persistent workspace state: all-zero on entry, all-zero again on exit (only M entries are touched), so
 // no per-call clear of a dense array and no per-point key/rank arrays exist.  HBM traffic ~= points + directions +
 // volume (+ records, mostly L2-resident between the kernels).
-struct FuseHdr { int n_big, max_cnt, n_over, scratch_cursor, pad[12]; };
+struct FuseHdr { int n_big, max_cnt, n_over, scratch_cursor, n_winners, pad[11]; };
 static_assert(sizeof(FuseHdr) == 64, "header size");
 typedef unsigned long long u64;
 constexpr int FUSE_CAP = 32;                 // entries per record
@@ -186,24 +179,36 @@ __device__ __forceinline__ int vf_warp_argmax(float mean, int k, bool valid) {
     return (int)__reduce_min_sync(0xffffffffu, (bits == mx && valid) ? (unsigned)k : 0x7fffffffu);
 }
 
-// winner's direction -> volume: flip to dir.y <= 0 (PMVO.py:702-703), then the frame HairGrowing works in
-__device__ __forceinline__ void store_winner(float4* __restrict__ volume, int key, float a, float b, float c) {
+// winner's direction: flip to dir.y <= 0 (PMVO.py:702-703), then the frame HairGrowing works in.  LIST: into the compact
+// winner list {dir, voxel key} at index w (the multi-GPU exchange format), else straight into the zero-filled volume
+template <bool LIST>
+__device__ __forceinline__ void store_winner(float4* __restrict__ out, int w, int key, float a, float b, float c) {
     if (b > 0.0f) { a = a * -1.0f; b = b * -1.0f; c = c * -1.0f; }
-    volume[key] = make_float4(a, -b, -c, 1.0f);
+    if (LIST) out[w] = make_float4(a, -b, -c, __int_as_float(key));
+    else out[key] = make_float4(a, -b, -c, 1.0f);
 }
 
 // CTA b walks the records allocated by binning block b (contiguous slots, so the hardware block scheduler does the load
 // balancing); warp w takes records w, w+8, ...  The next record's header / count / entries are loaded one record
 // ahead, and the winner's raw direction is fetched at the end of a record and stored into the (already zero-filled)
 // volume at the end of the next one, so no load is waited for where it is issued.
+template <bool LIST>
 __global__ void __launch_bounds__(MEDOID_WARPS * 32, 5)
 fuse_medoid_kernel(const int* __restrict__ block_cnt, const float4* __restrict__ records, FuseHdr* hdr,
-                   int2* __restrict__ big_list, u64* __restrict__ plane, const float* __restrict__ dirs,
-                   float4* __restrict__ volume) {
+                   int4* __restrict__ big_list, u64* __restrict__ plane, const float* __restrict__ dirs,
+                   float4* __restrict__ out) {
     __shared__ float4 s_u[MEDOID_WARPS][FUSE_CAP];
     __shared__ int4 s_ids[MEDOID_WARPS][FUSE_CAP / 4];
+    __shared__ int s_wbase;
     const int cnt = block_cnt[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int wbase = 0;
+    if (LIST) {                                          // the block's winners take consecutive list entries
+        if (cnt == 0) return;
+        if (threadIdx.x == 0) s_wbase = atomicAdd(&hdr->n_winners, cnt);
+        __syncthreads();
+        wbase = s_wbase;
+    }
     if (warp >= cnt) return;
     float4* u = s_u[warp];
     const int4* ids4 = s_ids[warp];
@@ -214,7 +219,7 @@ fuse_medoid_kernel(const int* __restrict__ block_cnt, const float4* __restrict__
     float4 e_n = rec[1 + lane];
     int K_n = (int)(__ldcg(plane + key_n) & 0xffffffffu);
     bool pend = false;                                   // lane 0: a winner whose direction load is in flight
-    int pend_key = 0;
+    int pend_key = 0, pend_w = 0;
     float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
     for (int ri = warp; ri < cnt; ri += MEDOID_WARPS, rec += STEP) {
         const int key = key_n, K = K_n;
@@ -274,28 +279,29 @@ fuse_medoid_kernel(const int* __restrict__ block_cnt, const float4* __restrict__
             __syncwarp();
         } else if (lane == 0) {
             // crowded voxel: left to fuse_medoid_big_kernel (keeps this kernel's register count low)
-            big_list[atomicAdd(&hdr->n_big, 1)] = make_int2((int)((int64_t)blockIdx.x * FUSE_BLOCK + ri), K);
+            big_list[atomicAdd(&hdr->n_big, 1)] = make_int4((int)((int64_t)blockIdx.x * FUSE_BLOCK + ri), K, wbase + ri, key);
         }
         if (more) K_n = (int)(__ldcg(plane + key_n) & 0xffffffffu);      // key_n has had a record's time to arrive
         if (lane == 0) {
-            if (pend) store_winner(volume, pend_key, p0, p1, p2);
+            if (pend) store_winner<LIST>(out, pend_w, pend_key, p0, p1, p2);
             pend = best_id >= 0;
             if (pend) {                                  // raw direction: consumed (flipped, stored) one record later
                 p0 = dirs[3 * best_id]; p1 = dirs[3 * best_id + 1]; p2 = dirs[3 * best_id + 2];
-                pend_key = key;
+                pend_key = key; pend_w = wbase + ri;
             }
             plane[key] = 0ull;                           // leave the plane clean for the next call
         }
     }
-    if (lane == 0 && pend) store_winner(volume, pend_key, p0, p1, p2);
+    if (lane == 0 && pend) store_winner<LIST>(out, pend_w, pend_key, p0, p1, p2);
 }
 
 // Records of more than CAP points (rare): one warp each; record + overflow chain gathered into global scratch, ranked
 // into point order there, generic torch.mean row sums.
+template <bool LIST>
 __global__ void __launch_bounds__(256)
 fuse_medoid_big_kernel(const float4* __restrict__ records, const int* __restrict__ over_head, const float4* __restrict__ over_ent,
-                       const int* __restrict__ over_next, FuseHdr* hdr, const int2* __restrict__ big_list, float4* scratch,
-                       const float* __restrict__ dirs, float4* __restrict__ volume) {
+                       const int* __restrict__ over_next, FuseHdr* hdr, const int4* __restrict__ big_list, float4* scratch,
+                       const float* __restrict__ dirs, float4* __restrict__ out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nbig = hdr->n_big;
     for (int bi = blockIdx.x * 8 + warp; bi < nbig; bi += gridDim.x * 8) {
@@ -333,12 +339,57 @@ fuse_medoid_big_kernel(const float4* __restrict__ records, const int* __restrict
             if (arg_better_max(ob, ok, best, bk)) { best = ob; bk = ok; }
         }
         if (lane == 0) {
-            float o0, o1, o2;
-            load_dir(dirs, __float_as_int(__ldcg(srt + bk).w), o0, o1, o2);
-            volume[reinterpret_cast<const int*>(rec)[0]] = make_float4(o0, -o1, -o2, 1.0f);
+            const int bid = __float_as_int(__ldcg(srt + bk).w);
+            store_winner<LIST>(out, big_list[bi].z, big_list[bi].w, dirs[3 * (int64_t)bid], dirs[3 * (int64_t)bid + 1], dirs[3 * (int64_t)bid + 2]);
         }
         __syncwarp();
     }
+}
+
+constexpr int FILL_CHUNK = 32768;            // bytes per TMA bulk store of the zero fill
+// Zero fill by TMA bulk stores: a zeroed shared-memory tile is the source of every store, so nothing has to be waited
+// for until the end; one issuing thread per CTA, one CTA per SM.
+__global__ void __launch_bounds__(32, 1)
+fill_bulk_kernel(unsigned char* __restrict__ dst, u64 bytes) {
+    extern __shared__ __align__(128) unsigned char zbuf[];
+    for (int t = threadIdx.x; t < FILL_CHUNK / 16; t += 32) reinterpret_cast<int4*>(zbuf)[t] = make_int4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> visible to the TMA unit
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(zbuf);
+        const u64 nchunks = (bytes + FILL_CHUNK - 1) / FILL_CHUNK;
+        // evict-first: the zero lines stream through L2 without displacing the records / winners the concurrent
+        // grouping and medoid kernels keep there
+        u64 pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        for (u64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            const u64 off = c * FILL_CHUNK;
+            const unsigned sz = (unsigned)((bytes - off < (u64)FILL_CHUNK) ? (bytes - off) : (u64)FILL_CHUNK);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         :: "l"(dst + off), "r"(saddr), "r"(sz), "l"(pol) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+// winners -> volume (already zero filled): 16 B per occupied voxel; entries with key < 0 are padding
+__global__ void __launch_bounds__(256)
+scatter_kernel(const float4* __restrict__ winners, int64_t count, int64_t nvox, float4* __restrict__ volume) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const float4 w = winners[t];
+        const int key = __float_as_int(w.w);
+        if (key >= 0 && key < nvox) volume[key] = make_float4(w.x, w.y, w.z, 1.0f);
+    }
+}
+
+// winner export: count out, unused capacity marked with key -1
+__global__ void __launch_bounds__(256)
+winners_finish_kernel(float4* __restrict__ winners, int64_t capacity, const FuseHdr* __restrict__ hdr, int* __restrict__ count_out) {
+    const int nw = hdr->n_winners;
+    for (int64_t t = nw + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < capacity; t += (int64_t)gridDim.x * blockDim.x)
+        winners[t] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && count_out) *count_out = nw;
 }
 
 __global__ void overwrite_kernel(VGrid g, const float* __restrict__ pts, const float* __restrict__ dirs, int64_t n,
@@ -412,7 +463,7 @@ VGrid make_grid(const double* vmin, double vs, int gx, int gy, int gz) {
 }  // namespace
 
 // per-call workspace: [hdr 64 B][over_head S int][block_cnt nb int][records S*(CAP+1) float4][over_ent n float4]
-// [scratch 2n float4][big_list n/CAP int2][over_next n int] with S = nb * 256 record slots, nb = ceil(n / 256)
+// [scratch 2n float4][big_list n/CAP int4][over_next n int] with S = nb * 256 record slots, nb = ceil(n / 256)
 namespace {
 // auxiliary stream for the volume zero fill (one per device and host thread)
 struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
@@ -433,7 +484,7 @@ int64_t fuse_nb(int64_t n) { return (n + FUSE_BLOCK - 1) / FUSE_BLOCK; }
 extern "C" int64_t mh_voxel_fuse_workspace_bytes(int64_t n, int32_t gx, int32_t gy, int32_t gz) {
     (void)gx; (void)gy; (void)gz;
     const int64_t nb = fuse_nb(n), S = nb * FUSE_BLOCK;
-    return 64 + 4 * (S + nb + 16) + 16 * (S * FUSE_STRIDE + 3 * n + 8) + 8 * (n / FUSE_CAP + 2) + 4 * (n + 4);
+    return 64 + 4 * (S + nb + 16) + 16 * (S * FUSE_STRIDE + 3 * n + 8) + 16 * (n / FUSE_CAP + 2) + 4 * (n + 4);
 }
 // persistent plane: 8 B per voxel {count | slot+1}, all-zero between calls
 extern "C" int64_t mh_voxel_fuse_plane_bytes(int32_t gx, int32_t gy, int32_t gz) { return 8 * (int64_t)gx * gy * gz; }
@@ -444,21 +495,34 @@ extern "C" int mh_voxel_fuse_plane_init(void* stream, void* plane, int32_t gx, i
     return 0;
 }
 
-extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, const uint8_t* valid, int64_t n,
-                             const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
-                             void* volume, int32_t* vox_index, void* plane, void* workspace, int64_t workspace_bytes) {
-    MH_CHECK_ARG(volume && workspace && plane && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
-    MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && voxel_size > 0, "bad grid");
-    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31) - 512, "grid or point count too large for int32 keys");
-    MH_CHECK_ARG(workspace_bytes >= mh_voxel_fuse_workspace_bytes(n, gx, gy, gz), "workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t nvox = (int64_t)gx * gy * gz;
-    float4* vol = reinterpret_cast<float4*>(volume);
-    if (n == 0) {
-        cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, st);
-        MH_CHECK_LAUNCH();
-        return 0;
+namespace {
+int fuse_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+// zero fill of `bytes` on stream s by TMA bulk stores, one CTA per SM (used where the fill has the GPU to itself: the
+// winner scatter of the multi-GPU path, empty inputs; the single-GPU fusion overlaps a memset with its binning kernel)
+void launch_fill(void* dst, size_t bytes, cudaStream_t s) {
+    if ((bytes & 15) || (reinterpret_cast<uintptr_t>(dst) & 15) || fuse_env("MH_FUSE_FILL", 1) == 0) { cudaMemsetAsync(dst, 0, bytes, s); return; }
+    static thread_local bool attr[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 15]) {
+        cudaFuncSetAttribute(fill_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_CHUNK);
+        attr[dev & 15] = true;
     }
+    const size_t nchunks = (bytes + FILL_CHUNK - 1) / FILL_CHUNK;
+    fill_bulk_kernel<<<(unsigned)std::min<size_t>((size_t)mh_sm_count(), nchunks), 32, FILL_CHUNK, s>>>(reinterpret_cast<unsigned char*>(dst), (u64)bytes);
+    MH_COUNT_LAUNCH();
+}
+
+// LIST = false: fused volume into `out` (float4 [gz][gy][gx]); LIST = true: winners into `out` (float4 [capacity]), their
+// number into *count, unused capacity marked with key -1
+template <bool LIST>
+int fuse_run(cudaStream_t st, const float* points, const float* dirs, const uint8_t* valid, int64_t n, const double* voxel_min_host,
+             double voxel_size, int32_t gx, int32_t gy, int32_t gz, float4* out, int64_t capacity, int32_t* count,
+             int32_t* vox_index, void* plane, void* workspace) {
+    const int64_t nvox = (int64_t)gx * gy * gz;
     const int64_t nb = fuse_nb(n), S = nb * FUSE_BLOCK;
     const VGrid g = make_grid(voxel_min_host, voxel_size, gx, gy, gz);
     FuseHdr* hdr = reinterpret_cast<FuseHdr*>(workspace);
@@ -467,28 +531,89 @@ extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dir
     float4* records = reinterpret_cast<float4*>(block_cnt + ((nb + 3) / 4) * 4);
     float4* over_ent = records + S * FUSE_STRIDE;
     float4* scratch = over_ent + (n + 1);
-    int2* big_list = reinterpret_cast<int2*>(scratch + (2 * n + 2));       // at most n / CAP records overflow
+    int4* big_list = reinterpret_cast<int4*>(scratch + (2 * n + 2));       // at most n / CAP records overflow
     int* over_next = reinterpret_cast<int*>(big_list + (n / FUSE_CAP + 2));
     u64* pl = reinterpret_cast<u64*>(plane);
     // The zero fill of the volume (201 MB at 256x256x192: the only bandwidth-sized term) is a memset on an auxiliary
     // stream, concurrent with the latency-bound binning kernel; the medoid kernel, which writes the results into the
-    // volume, joins it first.  (Streaming the fill from the binning / medoid kernels' own threads was measured: it is
-    // additive there, profiles/r1_summary.md.)
+    // volume, joins it first.  Measured alternatives (profiles/r2_fuse.md): streaming the fill from the binning / medoid
+    // kernels' own threads is additive; a fill that keeps running underneath the medoid kernel (TMA bulk stores from one
+    // CTA per SM, winners deferred to a scatter kernel) slows both sides by more than the overlap gains.
     AuxStream& ax = aux_stream();
-    cudaEventRecord(ax.fork, st);
-    cudaStreamWaitEvent(ax.s, ax.fork, 0);
-    cudaMemsetAsync(volume, 0, sizeof(float4) * nvox, ax.s);
-    cudaEventRecord(ax.join, ax.s);
+    if (!LIST) {
+        cudaEventRecord(ax.fork, st);
+        cudaStreamWaitEvent(ax.s, ax.fork, 0);
+        cudaMemsetAsync(out, 0, sizeof(float4) * nvox, ax.s);
+        cudaEventRecord(ax.join, ax.s);
+    }
     cudaMemsetAsync(hdr, 0, sizeof(FuseHdr) + sizeof(int) * (S + nb), st);  // header, overflow chain heads, per-block record counts
     bin_kernel<<<(unsigned)nb, FUSE_BLOCK, 0, st>>>(g, 1.0 / voxel_size, points, dirs, valid, n, pl, records, over_head, over_ent,
                                                     over_next, block_cnt, hdr, vox_index);
     MH_COUNT_LAUNCH();
-    cudaStreamWaitEvent(st, ax.join, 0);
-    fuse_medoid_kernel<<<(unsigned)nb, MEDOID_WARPS * 32, 0, st>>>(block_cnt, records, hdr, big_list, pl, dirs, vol);
+    if (!LIST) cudaStreamWaitEvent(st, ax.join, 0);
+    fuse_medoid_kernel<LIST><<<(unsigned)nb, MEDOID_WARPS * 32, 0, st>>>(block_cnt, records, hdr, big_list, pl, dirs, out);
     MH_COUNT_LAUNCH();
-    fuse_medoid_big_kernel<<<(unsigned)std::min<int64_t>((int64_t)mh_sm_count() * 4, n / (8 * FUSE_CAP) + 1), 256, 0, st>>>(
-        records, over_head, over_ent, over_next, hdr, big_list, scratch, dirs, vol);
+    fuse_medoid_big_kernel<LIST><<<(unsigned)std::min<int64_t>((int64_t)mh_sm_count() * 4, n / (8 * FUSE_CAP) + 1), 256, 0, st>>>(
+        records, over_head, over_ent, over_next, hdr, big_list, scratch, dirs, out);
     MH_COUNT_LAUNCH();
+    if (LIST) {
+        winners_finish_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)mh_sm_count() * 2, (capacity + 255) / 256)), 256, 0, st>>>(
+            out, capacity, hdr, count);
+        MH_COUNT_LAUNCH();
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int mh_voxel_fuse(void* stream, const float* points, const float* dirs, const uint8_t* valid, int64_t n,
+                             const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
+                             void* volume, int32_t* vox_index, void* plane, void* workspace, int64_t workspace_bytes) {
+    MH_CHECK_ARG(volume && workspace && plane && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
+    MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && voxel_size > 0, "bad grid");
+    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31) - 512, "grid or point count too large for int32 keys");
+    MH_CHECK_ARG(workspace_bytes >= mh_voxel_fuse_workspace_bytes(n, gx, gy, gz), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) launch_fill(volume, sizeof(float4) * (size_t)gx * gy * gz, st);
+    else fuse_run<false>(st, points, dirs, valid, n, voxel_min_host, voxel_size, gx, gy, gz, reinterpret_cast<float4*>(volume), 0, nullptr,
+                         vox_index, plane, workspace);
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_voxel_fuse_winners(void* stream, const float* points, const float* dirs, const uint8_t* valid, int64_t n,
+                                     const double* voxel_min_host, double voxel_size, int32_t gx, int32_t gy, int32_t gz,
+                                     void* winners /*float4 [capacity]*/, int64_t capacity, int32_t* count, int32_t* vox_index,
+                                     void* plane, void* workspace, int64_t workspace_bytes) {
+    MH_CHECK_ARG(winners && count && workspace && plane && voxel_min_host && (n == 0 || (points && dirs)), "null pointer");
+    MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && voxel_size > 0, "bad grid");
+    MH_CHECK_ARG((int64_t)gx * gy * gz < (1ll << 31) && n < (1ll << 31) - 512, "grid or point count too large for int32 keys");
+    MH_CHECK_ARG(capacity >= std::min<int64_t>(n, (int64_t)gx * gy * gz), "winner capacity below min(n, voxels)");
+    MH_CHECK_ARG(workspace_bytes >= mh_voxel_fuse_workspace_bytes(n, gx, gy, gz), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        cudaMemsetAsync(workspace, 0, sizeof(FuseHdr), st);
+        winners_finish_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)mh_sm_count() * 2, (capacity + 255) / 256)), 256, 0, st>>>(
+            reinterpret_cast<float4*>(winners), capacity, reinterpret_cast<const FuseHdr*>(workspace), count);
+        MH_COUNT_LAUNCH();
+    } else {
+        fuse_run<true>(st, points, dirs, valid, n, voxel_min_host, voxel_size, gx, gy, gz, reinterpret_cast<float4*>(winners), capacity, count,
+                       vox_index, plane, workspace);
+    }
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mh_voxel_scatter(void* stream, const void* winners, int64_t m, int32_t gx, int32_t gy, int32_t gz, void* volume,
+                                int32_t zero_fill) {
+    MH_CHECK_ARG(volume && (m == 0 || winners) && gx > 0 && gy > 0 && gz > 0 && m >= 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nvox = (int64_t)gx * gy * gz;
+    if (zero_fill) launch_fill(volume, sizeof(float4) * nvox, st);
+    if (m > 0) {
+        scatter_kernel<<<(unsigned)std::min<int64_t>((int64_t)mh_sm_count() * 2, (m + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(winners), m, nvox, reinterpret_cast<float4*>(volume));
+        MH_COUNT_LAUNCH();
+    }
     MH_CHECK_LAUNCH();
     return 0;
 }

@@ -445,6 +445,50 @@ def voxel_fuse(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, v
     return (vol, vidx) if return_index else vol
 
 
+FUSE_HDR_BYTES = 0          # the persistent fusion plane has no header: all of it is zero between calls
+
+
+def voxel_fuse_winners(select_points, select_ori, dev, grid=GRID, voxel_min=VOXEL_MIN, voxel_size=VOXEL_SIZE, valid=None,
+                       capacity=None):
+    """The fusion up to the per-voxel winners (mh_voxel_fuse_winners): -> (winners float32 [capacity,4], count int32 [1])
+    on the device; entries past count carry key -1.  Multi-GPU exchange format of the fused volume."""
+    pts = torch.as_tensor(select_points).to(dev).type(torch.float).contiguous()
+    dirs = torch.as_tensor(select_ori).to(dev).type(torch.float).contiguous()
+    n = pts.size(0)
+    gx, gy, gz = [int(g) for g in grid]
+    cap = int(capacity) if capacity is not None else max(1, min(n, gx * gy * gz))
+    win = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    wsb = lib().mh_voxel_fuse_workspace_bytes(n, gx, gy, gz)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    vmin = np.ascontiguousarray(np.asarray(voxel_min, dtype=np.float64))
+    key, plane = fuse_plane(pts.device, grid)
+    if valid is not None:
+        valid = valid.to(dev).to(torch.uint8).contiguous()
+    try:
+        with torch.cuda.device(dev):
+            check(lib().mh_voxel_fuse_winners(stream_ptr(dev), ptr(pts), ptr(dirs), ptr(valid), n,
+                                              vmin.ctypes.data_as(C.c_void_p), float(voxel_size), gx, gy, gz, ptr(win), cap,
+                                              ptr(cnt), None, ptr(plane), ptr(ws), wsb), "mh_voxel_fuse_winners")
+    except Exception:
+        _FUSE_PLANES.pop(key, None)
+        raise
+    return win, cnt
+
+
+def voxel_scatter(winners, dev, grid=GRID, volume=None):
+    """winners float32 [m,4] -> float4 volume (zero filled first unless `volume` is given)."""
+    gx, gy, gz = [int(g) for g in grid]
+    zero = volume is None
+    if volume is None:
+        volume = torch.empty((gz, gy, gx, 4), dtype=torch.float32, device=dev)
+    winners = winners.contiguous()
+    with torch.cuda.device(dev):
+        check(lib().mh_voxel_scatter(stream_ptr(dev), ptr(winners), winners.size(0), gx, gy, gz, ptr(volume), 1 if zero else 0),
+              "mh_voxel_scatter")
+    return volume
+
+
 def volume_to_mat(vol):
     """float4 volume -> (Occ [gy,gx,gz], Ori [gy,gx,3*gz]) float64 device tensors, the arrays PMVO.py:763-764 saves."""
     gz, gy, gx, _ = vol.shape

@@ -238,7 +238,7 @@ def test_voxel_fuse_crowded_voxels_vs_oracle():
     assert same[occ_o > 0].mean() >= 0.99
     assert same[occ_o == 0].all()
     _, plane = P.fuse_plane(torch.device("cuda:0"), P.GRID)
-    assert int(plane.view(torch.int64).abs().max().item()) == 0
+    assert int(plane[P.FUSE_HDR_BYTES:].view(torch.int64).abs().max().item()) == 0
 
 
 def test_knn_exact_vs_kdtree():
@@ -283,3 +283,26 @@ def test_empty_and_single_inputs(case):
     far = np.array([[5.0, 5.0, 5.0]])                                   # out of every image: invisible everywhere
     s, sp, f = pmvo.filter_points(torch.from_numpy(far).float())
     assert not bool(s[0]) and not bool(f[0])
+
+
+def test_voxel_fuse_winner_exchange_equals_dense_fusion():
+    """the multi-GPU exchange format: disjoint voxel slabs fused to winner lists, concatenated and scattered, give the
+    single fusion's volume bit for bit (what pipeline.fuse_stage does across ranks)."""
+    from monohair_b200 import pmvo as P
+    rng = np.random.default_rng(5)
+    n = 60000
+    pts = (rng.normal(size=(n, 3)) * np.array([0.05, 0.06, 0.05])).astype(np.float32)
+    dirs = rng.normal(size=(n, 3)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    tp, td = torch.from_numpy(pts).to(dev), torch.from_numpy(dirs).to(dev)
+    vol = P.voxel_fuse(tp, td, dev)
+    z = torch.round((-(tp[:, 2].double()) - float(P.VOXEL_MIN[2])) / float(P.VOXEL_SIZE)).clamp_(0, P.GRID[2] - 1).long()
+    parts = []
+    for a, b in ((0, 90), (90, 100), (100, 192)):
+        win, cnt = P.voxel_fuse_winners(tp, td, dev, valid=(z >= a) & (z < b))
+        c = int(cnt.item())
+        assert bool((win[c:, 3].view(torch.int32) == -1).all()) and bool((win[:c, 3].view(torch.int32) >= 0).all())
+        parts.append(win)                                  # padded entries (key -1) are skipped by the scatter
+    vol2 = P.voxel_scatter(torch.cat(parts, 0), dev)
+    assert torch.equal(vol, vol2)
+    assert int(vol[..., 3].sum().item()) > 1000

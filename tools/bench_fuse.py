@@ -48,14 +48,17 @@ def main():
             ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts))
         occ = int(vol[..., 3].sum().item())
-        clean = int(plane.view(torch.int64).abs().max().item()) == 0
-        hdr = ws[:64].view(torch.int32).cpu().numpy()
+        clean = int(plane[P.FUSE_HDR_BYTES:].view(torch.int64).abs().max().item()) == 0
+        hdr = ws[:64].view(torch.int32).cpu().numpy()[[0, 1, 2, 4]]
         same = True
         if ref is None:
             ref = vol.clone()
         else:
             same = bool(torch.equal(ref, vol))
-        print(f"voxel_fuse: n={n} occupied={occ} crowded-max={hdr[1]} overflow={hdr[2]} median {ms*1e3:.1f} us min {min(ts)*1e3:.1f} us  "
+        win, cnt = P.voxel_fuse_winners(pts, dirs, dev)
+        vol2 = P.voxel_scatter(win[: int(cnt.item())], dev)
+        same = same and bool(torch.equal(vol2, vol))
+        print(f"voxel_fuse: n={n} occupied={occ} crowded-max={hdr[1]} winners={hdr[3]} median {ms*1e3:.1f} us min {min(ts)*1e3:.1f} us  "
               f"algorithmic {alg/1e6:.1f} MB -> {alg/ms/1e6:.0f} GB/s = {alg/ms/1e6/6553:.1%} of 6553  plane_clean={clean} same_volume={same}")
         del ws
 
