@@ -10,7 +10,7 @@ import torch
 
 from monohair_b200 import options
 from monohair_b200.hairgrow import HairGrowing, points_to_voxel, save_hair_strands, smooth_strands, voxel_to_points  # noqa: F401
-from monohair_b200.pmvo_utils import read_obj, sample_points_uniformly
+from monohair_b200.pmvo_utils import read_obj, read_obj_normals, sample_points_uniformly  # noqa: F401
 
 
 def config_parser():
@@ -35,8 +35,8 @@ def config_parser():
 
 def main():
     args = config_parser()
-    v, f = read_obj(args.data.scalp_path)
-    scalp_points, scalp_normals = sample_points_uniformly(v, f, 60000, with_normals=True)
+    v, f, vn = read_obj_normals(args.data.scalp_path)            # open3d read_triangle_mesh: `vn` records as vertex normals
+    scalp_points, scalp_normals = sample_points_uniformly(v, f, 60000, with_normals=True, vertex_normals=vn)   # use_triangle_normal=False
     scalp_points += args.bust_to_origin
     scalp_points = torch.from_numpy(scalp_points).to(args.device)
     scalp_normals = torch.from_numpy(scalp_normals).to(args.device)

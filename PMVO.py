@@ -17,9 +17,14 @@ def main():
     args = config_parser()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
+        # one process per GPU: every rank loads the capture, rank 0 samples the candidates (the sampler draws random
+        # numbers) and broadcasts them, the point-parallel stages are sharded (monohair_b200/pipeline.py) and rank 0
+        # alone writes the files; the other ranks read them back behind a barrier where the reference re-reads its own
         import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        args.device = f"cuda:{local}"
     rank = int(os.environ.get("RANK", "0"))
     _impl.device = args.device
     _impl.args = args
@@ -43,8 +48,11 @@ def main():
 
     if args.PMVO.optimize:
         print('load raw mesh...')
-        points = load_colmap_points(args.data.raw_points_path, args.bbox_min, args.bust_to_origin, 0.005 / 4,
-                                    [512, 512, 384], True, args.PMVO.num_sample_per_grid)
+        points = None
+        if rank == 0:
+            points = load_colmap_points(args.data.raw_points_path, args.bbox_min, args.bust_to_origin, 0.005 / 4,
+                                        [512, 512, 384], True, args.PMVO.num_sample_per_grid)
+        points = _impl.broadcast_array(points, args.device)
         raw_points = points.copy()
         print('total points:', points.shape[0])
         if args.PMVO.filter_point:
@@ -52,12 +60,13 @@ def main():
             surface_index, surface_points, filter_index = filter_negative_points(points, pmvo, args)
             n_cov = surface_index.shape[0]
             points = surface_points
-            os.makedirs(args.save_root, exist_ok=True)
-            np.save(os.path.join(args.save_root, 'surface.npy'), raw_points[:n_cov][surface_index])
-            np.save(os.path.join(args.save_root, 'filter_unvisible.npy'), raw_points[:n_cov][filter_index])
+            if rank == 0:
+                os.makedirs(args.save_root, exist_ok=True)
+                np.save(os.path.join(args.save_root, 'surface.npy'), raw_points[:n_cov][surface_index])
+                np.save(os.path.join(args.save_root, 'filter_unvisible.npy'), raw_points[:n_cov][filter_index])
         _impl.Num_points = points.shape[0]
         print('process points:', _impl.Num_points)
-        optimize(points, pmvo, args)
+        optimize(points, pmvo, args)                 # rank 0 writes optimize/*.npy, then a barrier
         select_points = np.load(args.save_root + '/select_p.npy')
         select_ori = np.load(args.save_root + '/select_o.npy')
         min_loss = np.load(args.save_root + '/min_loss.npy')
@@ -71,6 +80,10 @@ def main():
         filter_unvisible_points = np.load(args.save_root + '/filter_unvisible.npy')
         refine(select_points, select_ori, min_loss, pmvo, filter_unvisible_points, args, infer_inner=args.PMVO.infer_inner,
                threshold=args.PMVO.threshold, genrate_ori_only=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

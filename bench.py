@@ -120,6 +120,13 @@ def cpu_port_step(vm, cand_sample, cfg, scalp):
     return len(sp), time.time() - t0
 
 
+def config_dict(cfg):
+    """the workload, in the same words for both arms (the driver compares the two `config` objects)."""
+    return {"workload": cfg["name"], "views": cfg["V"], "image": [cfg["H"], cfg["W"]], "patch": cfg["patch"],
+            "grid": [256, 256, 192], "num_sample_per_grid": cfg["num_per_grid"],
+            "cache": "inputs larger than L2 (%.1f GB of view maps, gathered)" % ((cfg["V"] * cfg["H"] * cfg["W"] * 32) / 1e9)}
+
+
 def cpu_sample(cand, n):
     """every (N/n)-th candidate of the covered range: same spatial distribution as the full job."""
     stride = max(1, cand.shape[0] // n)
@@ -147,8 +154,7 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": "pmvo_points_per_s", "value": val, "unit": "points/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "views": cfg["V"], "image": [cfg["H"], cfg["W"]], "patch": cfg["patch"],
-                       "grid": [256, 256, 192]},
+            "config": config_dict(cfg),
             "cpu_baseline": {"value": val, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{len(sample)} candidate points/step ({n_tot // max(args.steps,1)} optimised), "
                                        f"all {cfg['V']} views at full resolution; torch-CPU oracle port of the reference"},
@@ -168,7 +174,6 @@ def run_b200(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MH_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
@@ -238,6 +243,11 @@ def run_b200(args, cfg):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     n_opt = out["n_optimized"]
+    # bit-level checksums of the results (int32 view, summed in int64): equal across N means the sharded job reproduces
+    # the single-GPU one bit for bit
+    cks = lambda t: int(t.contiguous().view(torch.int32).to(torch.int64).sum().item())
+    checksums = {"volume": cks(out["volume"]), "select_o": cks(out["select_o"]), "min_loss": cks(out["min_loss"]),
+                 "refine_o": cks(out["refine_o"]), "occupied": int(out["volume"][..., 3].sum().item())}
     value = n_opt / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel (optimize) and of the HBM-bound ones --------------------------------
@@ -296,7 +306,7 @@ def run_b200(args, cfg):
         torch.cuda.empty_cache()
         kw2 = dict(image_size=[cfg["H"], cfg["W"]], patch_size=cfg["patch"], visible_threshold=cfg["visible_thr"],
                    conf_threshold=cfg["conf_thr"], threshold=cfg["thr"], device=dev)
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = max(1, args.steps)
         host = pipeline.pmvo_job_host(cams, h_depth, h_ori, h_conf, h_mask, h_cand, **kw2)      # warm-up
         barrier()
         t0 = time.time()
@@ -354,12 +364,13 @@ def run_b200(args, cfg):
         line = {"metric": "pmvo_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": cfg["name"], "views": cfg["V"], "image": [cfg["H"], cfg["W"]], "patch": cfg["patch"],
-                           "grid": [256, 256, 192], "candidates": stats["n_candidates"], "optimised": n_opt,
-                           "selected": stats["n_selected"], "near_surface": stats["n_fu"],
-                           "cache": "inputs larger than L2 (%.1f GB of resident view maps, gathered)" %
-                                    ((cfg["V"] * cfg["H"] * cfg["W"] * 32) / 1e9),
-                           "parallelism": "1 GPU" if world == 1 else f"points sharded over {world} GPUs + volume all-reduce"},
+                "config": config_dict(cfg),
+                "run": {"candidates": stats["n_candidates"], "optimised": n_opt, "selected": stats["n_selected"],
+                        "near_surface": stats["n_fu"],
+                        "parallelism": "1 GPU" if world == 1 else
+                        f"points sharded over {world} GPUs (filter, forward, kNN, re-score, near-surface medoids); "
+                        f"fusion {os.environ.get('MH_FUSE_DIST', 'replicated')}"},
+                "checksums": checksums,
                 "stage_ms": med, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks}
         print(json.dumps(line), flush=True)

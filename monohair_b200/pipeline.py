@@ -3,13 +3,17 @@
 wraps this and writes the reference's files; bench.py times it.
 
 Multi-GPU (one process per GPU, torch.distributed/NCCL): every rank holds all views; the candidate points are
-sharded by index for filter_points / forward (no data-path collective, results all-gathered), the kNN of the
-refine stage is sharded by query, and the voxel fusion is sharded by voxel slab with ONE all-reduce(SUM) of the
-fused volume (disjoint support, so the sum is exact) -- SURVEY.md §8e.
+sharded by index for filter_points / forward (no data-path collective, results all-gathered), the kNN queries, the
+head filter, the re-scoring and the near-surface medoids are sharded by point (12 B centres are gathered, not the
+400 B neighbour lists), and the voxel fusion either runs replicated (its inputs are replicated by then and the whole
+fusion costs 0.12 ms, less than any collective) or -- MH_FUSE_DIST=winners, the form a job with rank-private points
+needs -- sharded by voxel slab with an all-gather of the per-voxel winners (16 B per occupied voxel; the union is the
+all-reduce(SUM) of the disjoint dense volumes, without moving 201 MB of zeros) -- SURVEY.md §8e.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -137,12 +141,27 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
     return o_new, l
 
 
-def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE, valid=None):
-    """Voxel fusion; with several ranks each fuses the points whose voxel z-slab it owns into a zeroed volume and
-    the volumes are summed with one all-reduce over NVLink.  `valid` masks points out without compacting them."""
-    dev = pm.device
+def medoid_stage(ori, nbr_fn, n, dev):
+    """medoid orientation of each query's neighbours, sharded by query: nbr_fn(a, b) -> int32 [b-a, K] neighbour
+    indices of queries a..b; only the 12 B centres are gathered."""
     dist = _dist()
     if dist is None:
+        return P.medoid_gather(ori, nbr_fn(0, n), dev)
+    r, w = dist.get_rank(), dist.get_world_size()
+    a, b = _shard(n, r, w)
+    c = P.medoid_gather(ori, nbr_fn(a, b), dev) if b > a else ori.new_zeros((0, 3))
+    return _all_gather_rows(c, n, w, dist).contiguous()
+
+
+def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE, valid=None, mode=None):
+    """Voxel fusion.  Several ranks, mode "replicated" (default: the inputs are replicated at this point of the job):
+    every rank fuses everything, no collective.  Mode "winners": each rank fuses the points whose voxel z-slab it owns
+    down to the per-voxel winners, the winner lists are all-gathered over NVLink and every rank scatters the union
+    into its zero-filled volume."""
+    dev = pm.device
+    dist = _dist()
+    mode = mode or os.environ.get("MH_FUSE_DIST", "replicated")
+    if dist is None or mode == "replicated":
         return P.voxel_fuse(pts, dirs, dev, grid, voxel_min, voxel_size, valid=valid)
     r, w = dist.get_rank(), dist.get_world_size()
     gz = int(grid[2])
@@ -152,9 +171,13 @@ def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.V
     mine = (z >= za) & (z < zb)
     if valid is not None:
         mine &= valid.bool()
-    vol = P.voxel_fuse(pts, dirs, dev, grid, voxel_min, voxel_size, valid=mine)
-    dist.all_reduce(vol, op=dist.ReduceOp.SUM)
-    return vol
+    win, cnt = P.voxel_fuse_winners(pts, dirs, dev, grid, voxel_min, voxel_size, valid=mine)
+    counts = torch.empty((w,), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(counts, cnt)
+    m = max(int(counts.max().item()), 1)                    # one host read: sizes the exchange
+    allw = torch.empty((w * m, 4), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(allw, win[:m].contiguous())  # entries past a rank's count carry key -1
+    return P.voxel_scatter(allw, dev, grid)
 
 
 def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
@@ -176,9 +199,8 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
     sp, so = pts[sel].contiguous(), o2[sel].contiguous()
     dev = pm.device
     if fu.size(0) > 0 and sp.size(0) >= 100:
-        nbr = knn_stage(sp, fu, 100, dev)
         fh = head_filter_stage(pm, fu, pm.visible_threshold)
-        center = P.medoid_gather(so, nbr, dev)
+        center = medoid_stage(so, lambda a, b: P.knn(sp, fu[a:b].contiguous(), 100, dev), fu.size(0), dev)
         # the head-filtered points are masked out of the fusion instead of being compacted away first: the compaction
         # needs a host synchronisation, which would expose the launch latency of the whole fusion
         all_p, all_o = torch.cat([sp, fu], 0), torch.cat([so, center], 0)

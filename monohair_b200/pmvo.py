@@ -44,6 +44,36 @@ def _world():
     return None, 0, 1
 
 
+def _rank0():
+    """True on the rank that writes the job's files (every rank when not distributed)."""
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
+def _barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def broadcast_array(a, dev, dtype=np.float64):
+    """rank 0's numpy array on every rank (shape first, then the data through the device)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return a
+    shp = torch.zeros((4,), dtype=torch.int64, device=dev)
+    if dist.get_rank() == 0:
+        a = np.ascontiguousarray(a, dtype=dtype)
+        shp[0] = a.ndim
+        shp[1:1 + a.ndim] = torch.tensor(a.shape, dtype=torch.int64)
+    dist.broadcast(shp, 0)
+    nd = int(shp[0].item())
+    shape = [int(v) for v in shp[1:1 + nd].tolist()]
+    t = torch.from_numpy(a).to(dev) if dist.get_rank() == 0 else torch.empty(shape, dtype=torch.from_numpy(np.zeros(1, dtype)).dtype, device=dev)
+    dist.broadcast(t, 0)
+    return t.cpu().numpy()
+
+
 SHARD_VIEW_UPLOAD = True   # multi-GPU: each rank uploads + packs only its block of views, planes are all-gathered over NVLink
 
 
@@ -319,7 +349,15 @@ class PMVO(nn.Module):
         rc = self._rowcol[v].long()
         oob = rc[:, 1] < 0
         col = torch.where(oob, -rc[:, 1] - 1, rc[:, 1])
-        return torch.stack([rc[:, 0], col], 1), None, oob
+        # z = -z_cam / 2 (PMVO.py:396) with z_cam the third row of pose @ [p;1]: the fp32 FMA chain of the kernels
+        # (mh_world_to_cam), evaluated here through float64 (each product is exact there), then rounded per step
+        pts = self._pts(points).double()
+        P = self.cam[v, 8:12].double().cpu().numpy()
+        z = torch.zeros_like(pts[:, 0])
+        for k in range(3):
+            z = (z + P[k] * pts[:, k]).float().double()
+        z = (z + P[3]).float()
+        return torch.stack([rc[:, 0], col], 1), z / -2.0, oob
 
 
 # ====================================================================================== module functions
@@ -331,8 +369,10 @@ def filter_negative_points(points, pmvo, args, step=30):
         step = step + 1
     num_sub_p = points.shape[0] // 30
     n_cov = min(step * num_sub_p, points.shape[0])
-    surface_index, surface_points, filter_index = pmvo.filter_points(
-        torch.from_numpy(points[:n_cov]).to(args.device).type(torch.float))
+    from . import pipeline
+    cand = torch.from_numpy(points[:n_cov]).to(args.device).type(torch.float)
+    surface_index, filter_index = pipeline.filter_stage(pmvo, cand, n_cov=n_cov)      # point-sharded under torchrun
+    surface_points = cand[surface_index]
     surface_points = surface_points.cpu().numpy()
     filter_indexs = filter_index.cpu().numpy()
     surface_indexs = surface_index.cpu().numpy()
@@ -350,18 +390,23 @@ def optimize(points, pmvo, args, chunk=1 << 20):
         sub = points[i:i + chunk]
         if sub.shape[0] == 0:
             continue
-        p, o, l, hc = pmvo.forward(sub)
+        from . import pipeline
+        p = pmvo._pts(sub)
+        o, l, hc = pipeline.forward_stage(pmvo, p)                                     # point-sharded under torchrun
         for lst, t in zip(outs, (p, o, l, hc)):
             lst.append(t)
     select_points = torch.cat(outs[0], 0).cpu().numpy()
     select_ori = torch.cat(outs[1], 0).cpu().numpy()
     min_loss = torch.cat(outs[2], 0).cpu().numpy()
     high_conf_index = torch.cat(outs[3], 0).cpu().numpy()
-    os.makedirs(args.save_root, exist_ok=True)
-    np.save(args.save_root + '/select_p.npy', select_points)
-    np.save(args.save_root + '/select_o.npy', select_ori)
-    np.save(args.save_root + '/min_loss.npy', min_loss)
-    np.save(args.save_root + '/high_conf_index.npy', high_conf_index)
+    if _rank0():
+        os.makedirs(args.save_root, exist_ok=True)
+        np.save(args.save_root + '/select_p.npy', select_points)
+        np.save(args.save_root + '/select_o.npy', select_ori)
+        np.save(args.save_root + '/min_loss.npy', min_loss)
+        np.save(args.save_root + '/high_conf_index.npy', high_conf_index)
+    _barrier()
+    return select_points, select_ori, min_loss, high_conf_index      # (the reference returns nothing; the files are the contract)
 
 
 def knn(ref, query, k, dev):
@@ -521,10 +566,12 @@ def refine(points, ori, loss, pmvo, filter_unvisible_points, args, infer_inner=T
     if not genrate_ori_only:
         print('filter nosiy points...')
         p_d, o_d, l_d = refine_points(points, ori, loss, pmvo)
-        os.makedirs(args.output_path + '/refine', exist_ok=True)
-        np.save(args.output_path + '/refine/select_p.npy', np.asarray(points))
-        np.save(args.output_path + '/refine/select_o.npy', o_d.cpu().numpy())
-        np.save(args.output_path + '/refine/min_loss.npy', l_d.cpu().numpy())
+        if _rank0():
+            os.makedirs(args.output_path + '/refine', exist_ok=True)
+            np.save(args.output_path + '/refine/select_p.npy', np.asarray(points))
+            np.save(args.output_path + '/refine/select_o.npy', o_d.cpu().numpy())
+            np.save(args.output_path + '/refine/min_loss.npy', l_d.cpu().numpy())
+        _barrier()                                   # every rank re-reads rank 0's files, like the reference re-reads its own
 
     points = np.load(args.output_path + '/refine/select_p.npy')
     ori = np.load(args.output_path + '/refine/select_o.npy')
@@ -544,8 +591,9 @@ def refine(points, ori, loss, pmvo, filter_unvisible_points, args, infer_inner=T
     else:
         fu_ori = torch.zeros((0, 3), device=dev)
         fu_pts = torch.zeros((0, 3), device=dev)
-    np.save(args.output_path + '/refine/filter_unvisible.npy', fu_pts.cpu().numpy())
-    np.save(args.output_path + '/refine/filter_unvisible_ori.npy', fu_ori.cpu().numpy())
+    if _rank0():
+        np.save(args.output_path + '/refine/filter_unvisible.npy', fu_pts.cpu().numpy())
+        np.save(args.output_path + '/refine/filter_unvisible_ori.npy', fu_ori.cpu().numpy())
 
     all_ori = torch.cat([select_ori, fu_ori], 0)
     all_pts = torch.cat([select_points, fu_pts], 0)
@@ -566,13 +614,16 @@ def refine(points, ori, loss, pmvo, filter_unvisible_points, args, infer_inner=T
         with torch.cuda.device(dev):
             check(lib().mh_voxel_overwrite(stream_ptr(dev), ptr(up), ptr(uo), up.size(0), vmin.ctypes.data_as(C.c_void_p),
                                            float(VOXEL_SIZE), gx, gy, gz, ptr(vol), ptr(ws)), "mh_voxel_overwrite")
-        np.save(os.path.join(args.save_path, 'coarse.npy'), up.cpu().numpy())
-        np.save(os.path.join(args.save_path, 'coarse_ori.npy'), uo.cpu().numpy())
+        if _rank0():
+            np.save(os.path.join(args.save_path, 'coarse.npy'), up.cpu().numpy())
+            np.save(os.path.join(args.save_path, 'coarse_ori.npy'), uo.cpu().numpy())
 
-    occ, ori_m = volume_to_mat(vol)
-    path = args.save_path
-    scipy.io.savemat(os.path.join(path, 'Ori3D.mat'), {'Ori': ori_m.cpu().numpy()})
-    scipy.io.savemat(os.path.join(path, 'Occ3D.mat'), {'Occ': occ.cpu().numpy()})
+    if _rank0():
+        occ, ori_m = volume_to_mat(vol)
+        path = args.save_path
+        scipy.io.savemat(os.path.join(path, 'Ori3D.mat'), {'Ori': ori_m.cpu().numpy()})
+        scipy.io.savemat(os.path.join(path, 'Occ3D.mat'), {'Occ': occ.cpu().numpy()})
+    _barrier()
     if return_volume:
         return vol
 
@@ -584,7 +635,8 @@ def config_parser():
     args = options.set(opt_cmd=opt_cmd)
     args.output_path = os.path.join(args.data.root, args.data.case, args.output_root, args.name)
     os.makedirs(args.output_path, exist_ok=True)
-    options.save_options_file(args)
+    if int(os.environ.get("RANK", "0")) == 0:
+        options.save_options_file(args)
     args.data.root = os.path.join(args.data.root, args.data.case)
     args.bbox_min = np.array(args.bbox_min)
     args.bust_to_origin = np.array(args.bust_to_origin)

@@ -85,16 +85,59 @@ def read_obj(path):
     return np.array(vs, dtype=np.float64).reshape(-1, 3), np.array(fs, dtype=np.int64).reshape(-1, 3)
 
 
-def sample_points_uniformly(vertices, faces, number_of_points, rng=None, with_normals=False):
+def read_obj_normals(path):
+    """OBJ with per-vertex normals the way open3d's read_triangle_mesh presents them (HairGrow.py:879): the `vn` record
+    a face corner refers to becomes that vertex's normal (last corner wins); vertices no corner gives a normal to, or
+    files without `vn`, fall back to area-weighted face normals.  -> vertices [n,3], faces [m,3], vertex normals [n,3]."""
+    vs, vns, fs, fns = [], [], [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith('v '):
+                vs.append([float(x) for x in line.split()[1:4]])
+            elif line.startswith('vn '):
+                vns.append([float(x) for x in line.split()[1:4]])
+            elif line.startswith('f '):
+                toks = [tok.split('/') for tok in line.split()[1:]]
+                idx = [int(t[0]) for t in toks]
+                idx = [i - 1 if i > 0 else len(vs) + i for i in idx]
+                nid = [int(t[2]) if len(t) > 2 and t[2] != '' else 0 for t in toks]
+                nid = [i - 1 if i > 0 else (len(vns) + i if i < 0 else -1) for i in nid]
+                for k in range(1, len(idx) - 1):
+                    fs.append([idx[0], idx[k], idx[k + 1]])
+                    fns.append([nid[0], nid[k], nid[k + 1]])
+    v = np.array(vs, dtype=np.float64).reshape(-1, 3)
+    fa = np.array(fs, dtype=np.int64).reshape(-1, 3)
+    a, b, c = v[fa[:, 0]], v[fa[:, 1]], v[fa[:, 2]]
+    fn = np.cross(b - a, c - a)                                  # length = 2 x area: area weighting for free
+    vn = np.zeros_like(v)
+    for k in range(3):
+        np.add.at(vn, fa[:, k], fn)
+    vn /= np.maximum(np.linalg.norm(vn, axis=1, keepdims=True), 1e-20)
+    if vns:
+        table = np.array(vns, dtype=np.float64).reshape(-1, 3)
+        fna = np.array(fns, dtype=np.int64).reshape(-1, 3)
+        ok = fna >= 0
+        vn[fa[ok]] = table[fna[ok]]                              # numpy scatter: the last corner written wins
+    return v, fa, vn
+
+
+def sample_points_uniformly(vertices, faces, number_of_points, rng=None, with_normals=False, vertex_normals=None):
     """area-weighted uniform surface sampling (stands in for open3d's sample_points_uniformly, whose RNG is
-    unseeded in the reference, PMVO_utils.py:346 / HairGrow.py:881)."""
-    rng = np.random.default_rng() if rng is None else rng
+    unseeded in the reference, PMVO_utils.py:346 / HairGrow.py:881).  With `vertex_normals` the returned normals are
+    the barycentric blend of the triangle's vertex normals with the sampling weights, un-normalised -- what open3d
+    returns for use_triangle_normal=False (HairGrow.py:880-881); otherwise flat face normals."""
+    # default: a generator seeded from numpy's global state, which options.process_options seeds (seed: 0), so a run is
+    # repeatable (open3d's own sampler is unseeded in the reference)
+    rng = np.random.default_rng(int(np.random.randint(0, 2 ** 31 - 1))) if rng is None else rng
     a, b, c = vertices[faces[:, 0]], vertices[faces[:, 1]], vertices[faces[:, 2]]
     n = np.cross(b - a, c - a)
     area = 0.5 * np.linalg.norm(n, axis=1)
     tri = rng.choice(len(faces), size=number_of_points, p=area / area.sum())
     r1, r2 = np.sqrt(rng.random(number_of_points)), rng.random(number_of_points)
     pts = (1 - r1)[:, None] * a[tri] + (r1 * (1 - r2))[:, None] * b[tri] + (r1 * r2)[:, None] * c[tri]
+    if with_normals and vertex_normals is not None:
+        n0, n1, n2 = vertex_normals[faces[tri, 0]], vertex_normals[faces[tri, 1]], vertex_normals[faces[tri, 2]]
+        return pts, (1 - r1)[:, None] * n0 + (r1 * (1 - r2))[:, None] * n1 + (r1 * r2)[:, None] * n2
     if with_normals:
         nn = n[tri] / np.maximum(np.linalg.norm(n[tri], axis=1, keepdims=True), 1e-20)
         return pts, nn

@@ -1,7 +1,8 @@
 """Run under torchrun on >= 2 GPUs (not collected by pytest):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
-Checks that the sharded PMVO job (points sharded, volume all-reduce over NCCL) reproduces the single-GPU job
-bit-for-bit: every stage is per-point / per-voxel independent, so sharding must not change a single value."""
+Checks that the sharded PMVO job (points sharded over the ranks; fusion replicated or, with MH_FUSE_DIST=winners, sharded
+by voxel slab with an all-gather of the per-voxel winners over NCCL) reproduces the single-GPU job bit-for-bit: every
+stage is per-point / per-voxel independent, so sharding must not change a single value.  Run by tests/test_gpu_multi.py."""
 import os
 import sys
 
@@ -54,6 +55,7 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if dist.get_rank() == 0:
         print("MULTI_GPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", "world", dist.get_world_size(),
+              "fusion", os.environ.get("MH_FUSE_DIST", "replicated"),
               "occupied voxels", int(multi["volume"][..., 3].sum().item()))
     dist.destroy_process_group()
     sys.exit(0 if int(t.item()) == 1 else 1)

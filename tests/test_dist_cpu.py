@@ -82,7 +82,28 @@ def _worker(rank, world, port, q):
         for i in torch.nonzero(keep)[:, 0].tolist():                 # "last point of a slab wins": any per-voxel rule will do
             vol[z[i], 0, 0] = torch.cat([dirs[i], torch.ones(1)])
         return vol
-    P.knn, P.voxel_fuse = cpu_knn, cpu_fuse
+
+    def cpu_winners(pts, dirs, dev, grid, voxel_min, voxel_size, valid=None, capacity=None):
+        gx, gy, gz = [int(v) for v in grid]
+        vol = cpu_fuse(pts, dirs, dev, grid, voxel_min, voxel_size, valid=valid).view(-1, 4)
+        keys = torch.nonzero(vol[:, 3] > 0)[:, 0]
+        cap = pts.size(0)
+        win = torch.zeros((cap, 4))
+        win[:, 3] = torch.full((cap,), -1, dtype=torch.int32).view(torch.float32)
+        win[: keys.numel(), :3] = vol[keys, :3]
+        win[: keys.numel(), 3] = keys.int().view(torch.float32)
+        return win, torch.tensor([keys.numel()], dtype=torch.int32)
+
+    def cpu_scatter(winners, dev, grid, volume=None):
+        gx, gy, gz = [int(v) for v in grid]
+        vol = torch.zeros((gz * gy * gx, 4))
+        k = winners[:, 3].contiguous().view(torch.int32).long()
+        ok = k >= 0
+        vol[k[ok], :3] = winners[ok, :3]
+        vol[k[ok], 3] = 1.0
+        return vol.view(gz, gy, gx, 4)
+    P.knn, P.voxel_fuse, P.voxel_fuse_winners, P.voxel_scatter = cpu_knn, cpu_fuse, cpu_winners, cpu_scatter
+    P.medoid_gather = lambda ori, nbr, dev: ori[nbr[:, 0].long()].contiguous()
     pm = FakePM()
     g = torch.Generator().manual_seed(5)
     pts = torch.rand((1003, 3), generator=g) - 0.4
@@ -91,18 +112,24 @@ def _worker(rank, world, port, q):
     grid, vmin, vs = (2, 2, 24), (-0.32, -0.32, -0.6), 0.05
     multi = (PL.forward_stage(pm, pts), PL.filter_stage(pm, pts), PL.head_filter_stage(pm, pts, 1),
              PL.knn_stage(pts[:200], pts, 7, pm.device), PL.fuse_stage(pm, pts, dirs, grid, vmin, vs, valid=valid),
-             PL.fuse_stage(pm, pts, dirs, grid, vmin, vs))
+             PL.fuse_stage(pm, pts, dirs, grid, vmin, vs),
+             PL.fuse_stage(pm, pts, dirs, grid, vmin, vs, valid=valid, mode="winners"),
+             PL.fuse_stage(pm, pts, dirs, grid, vmin, vs, mode="winners"),
+             PL.medoid_stage(dirs, lambda a, b: cpu_knn(pts[:200], pts[a:b], 7, pm.device), pts.size(0), pm.device))
     PL._FORCE_SINGLE = True
     single = (PL.forward_stage(pm, pts), PL.filter_stage(pm, pts), PL.head_filter_stage(pm, pts, 1),
               PL.knn_stage(pts[:200], pts, 7, pm.device), PL.fuse_stage(pm, pts, dirs, grid, vmin, vs, valid=valid),
-              PL.fuse_stage(pm, pts, dirs, grid, vmin, vs))
+              PL.fuse_stage(pm, pts, dirs, grid, vmin, vs),
+              PL.fuse_stage(pm, pts, dirs, grid, vmin, vs, valid=valid), PL.fuse_stage(pm, pts, dirs, grid, vmin, vs),
+              PL.medoid_stage(dirs, lambda a, b: cpu_knn(pts[:200], pts[a:b], 7, pm.device), pts.size(0), pm.device))
     PL._FORCE_SINGLE = False
 
     def same(a, b):
         if isinstance(a, (tuple, list)):
             return all(same(x, y) for x, y in zip(a, b))
         return torch.equal(a, b)
-    for name, m, s1 in zip(("forward", "filter", "head_filter", "knn", "fuse(valid)", "fuse"), multi, single):
+    for name, m, s1 in zip(("forward", "filter", "head_filter", "knn", "fuse(valid)", "fuse", "fuse winners(valid)", "fuse winners",
+                            "medoid"), multi, single):
         assert same(m, s1), f"{name}_stage: sharded result differs from the single-rank result"
     q.put((rank, "ok"))
     dist.destroy_process_group()

@@ -85,3 +85,26 @@ def test_strand_split_matches_per_strand_slicing():
     want = [pts2[off2[i]: off2[i] + lengths[i]] for i in range(n) if keep[i]]
     assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
     assert HairGrowing._split(pts, offsets, lengths, torch.zeros(n, dtype=torch.bool)) == []
+
+
+def test_scalp_normals_interpolate_vertex_normals(tmp_path):
+    """HairGrow.py:879-881: open3d returns the barycentric blend of the OBJ's `vn` records (use_triangle_normal=False),
+    not the face normal, whose sign would follow the face winding."""
+    import numpy as np
+    from monohair_b200.pmvo_utils import read_obj_normals, sample_points_uniformly
+    p = tmp_path / "tri.obj"
+    # one triangle wound so that its face normal is -z, with vn records pointing to +z-ish directions
+    p.write_text("v 0 0 0\nv 0 1 0\nv 1 0 0\nvn 0 0 1\nvn 0 0.6 0.8\nvn 0.6 0 0.8\nf 1//1 2//2 3//3\n")
+    v, f, vn = read_obj_normals(str(p))
+    assert np.allclose(vn, [[0, 0, 1], [0, 0.6, 0.8], [0.6, 0, 0.8]])
+    pts, nrm = sample_points_uniformly(v, f, 500, rng=np.random.default_rng(1), with_normals=True, vertex_normals=vn)
+    assert (nrm[:, 2] > 0.79).all()                                    # never the (-z) face normal
+    # the blend uses the same barycentric weights as the position: for this triangle point = (w2, w1, 0)
+    w1, w2 = pts[:, 1], pts[:, 0]
+    expect = (1 - w1 - w2)[:, None] * vn[0] + w1[:, None] * vn[1] + w2[:, None] * vn[2]
+    assert np.allclose(nrm, expect, atol=1e-12)
+    # no vn records: area-weighted vertex normals
+    q = tmp_path / "quad.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    v, f, vn = read_obj_normals(str(q))
+    assert np.allclose(vn, [[0, 0, 1]] * 4)
