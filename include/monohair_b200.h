@@ -245,6 +245,11 @@ int mh_dog_f64(void* stream, const double* image, int32_t H, int32_t W, const do
 /* order of torch.topk(k=20, dim=0, largest, sorted) on CPU for one column of V values (PMVO.py:341). */
 int mh_debug_topk_host(const float* values_host, int32_t V, int32_t k, int32_t* idx_host, float* val_host);
 
+/* GPU test hook: number of (a0, a1, b) triples for which the shared-reciprocal division of the projection code
+ * (mh_common.cuh: mh_div2) differs in any bit from the IEEE quotients a0/b, a1/b; added to *mismatches (uint64). */
+int mh_debug_div2_check(void* stream, const float* a0, const float* a1, const float* b, int64_t n,
+                        unsigned long long* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ _SIGS = {
     "mh_filterbank_wrap_f64": (C.c_int, [p, p, i32, i32, p, i32, i32, p]),
     "mh_dog_f64": (C.c_int, [p, p, i32, i32, p, i32, p, i32, p, p]),
     "mh_debug_topk_host": (C.c_int, [p, i32, i32, p, p]),
+    "mh_debug_div2_check": (C.c_int, [p, p, p, p, i64, p]),
 }
 
 

@@ -40,3 +40,25 @@ extern "C" int mh_debug_topk_host(const float* values, int32_t V, int32_t k, int
     for (int j = 0; j < k; ++j) { idx[j] = q[j].i; val[j] = q[j].v; }
     return 0;
 }
+
+// test hook: count operand triples for which mh_div2 differs from (a0 / b, a1 / b) in any bit
+__global__ void div2_check_kernel(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ b,
+                                  int64_t n, unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float q0, q1;
+        mh_div2(a0[i], a1[i], b[i], q0, q1);
+        const float r0 = __fdiv_rn(a0[i], b[i]), r1 = __fdiv_rn(a1[i], b[i]);
+        bad += (__float_as_uint(q0) != __float_as_uint(r0)) + (__float_as_uint(q1) != __float_as_uint(r1));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+extern "C" int mh_debug_div2_check(void* stream, const float* a0, const float* a1, const float* b, int64_t n,
+                                   unsigned long long* mismatches) {
+    MH_CHECK_ARG(a0 && a1 && b && mismatches && n >= 0, "bad arguments");
+    if (n == 0) return 0;
+    div2_check_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(a0, a1, b, n, mismatches);
+    MH_COUNT_LAUNCH();
+    MH_CHECK_LAUNCH();
+    return 0;
+}

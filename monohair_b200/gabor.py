@@ -115,9 +115,11 @@ def calculate_orientation(image_dir, label_dir, save_root, filename=None, iter=1
     ori, best_ori, confidence = calOrientationGabor()(gray, None, iter, threshold=threshold)
     cv2.imwrite(os.path.join(save_root, 'best_ori', filename), best_ori[0].cpu().numpy().transpose(1, 2, 0) / math.pi * 180,
                 [int(cv2.IMWRITE_JPEG_QUALITY), 100])
-    # torchvision.utils.save_image: x*255 + 0.5, clamp, uint8
+    # torchvision.utils.save_image(confidence, path) (GaborFilter.py:208): make_grid repeats the single channel three
+    # times, x*255 + 0.5, clamp, uint8, then PIL writes the file in the format of the extension with PIL's defaults
+    # (JPEG quality 75 for .jpg/.JPG captures, lossless for .png)
     c8 = confidence[0, 0].mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8).cpu().numpy()
-    cv2.imwrite(os.path.join(save_root, 'conf', filename), c8)
+    Image.fromarray(np.repeat(c8[..., None], 3, axis=2)).save(os.path.join(save_root, 'conf', filename))
     o = ori[0].cpu().numpy().transpose(1, 2, 0)
     o = (o + 1) / 2
     H, W = o.shape[:2]
@@ -175,6 +177,36 @@ def calc_orients(img, kernels, device="cuda:0"):
         check(lib().mh_filterbank_wrap_f64(stream_ptr(filtered.device), ptr(filtered), H, W, ptr(bank_d), n, K, ptr(out)),
               "mh_filterbank_wrap_f64")
     return out
+
+
+def main(args, device="cuda:0"):
+    """calc_orientation_maps.py:51-92: the first image of args.img_path -> orientation / confidence files with the
+    reference's names, dtypes and cv2 encodings (float arrays handed to cv2.imwrite are rounded half-to-even and
+    saturated to 8 bit by OpenCV; the RGB->BGR conversion of :78 only touches `<basename>1.png`)."""
+    import cv2
+    from PIL import Image
+    os.makedirs(args.orient_dir, exist_ok=True)
+    os.makedirs(args.conf_dir, exist_ok=True)
+    kernels = generate_gabor_filters(args.sigma_x, args.sigma_y, args.freq, args.num_filters)
+    for img_name in sorted(os.listdir(args.img_path))[:1]:
+        basename = img_name.split('.')[0]
+        img = np.array(Image.open(os.path.join(args.img_path, img_name)))
+        mask = np.array(Image.open(os.path.join(args.mask_path, img_name)))
+        mask = mask / np.max(mask)                                       # computed and unused, as in the reference
+        F_orients = calc_orients(img, kernels, device=device)
+        orientation_map = F_orients.argmax(0).cpu().numpy()
+        orientation_map_rad = orientation_map / args.num_filters * math.pi
+        indices_cm2 = np.stack([np.cos(orientation_map_rad) * 0.5 + 0.5, np.sin(orientation_map_rad) * 0.5 + 0.5,
+                                np.zeros_like(orientation_map_rad)], axis=2)
+        indices_cm2 = indices_cm2.astype(np.float32) * 255
+        cv2.imwrite(f'{args.orient_dir}/{basename}_ori.png', indices_cm2)
+        indices_cm2 = cv2.cvtColor(indices_cm2, cv2.COLOR_RGB2BGR)
+        confidence_map = calc_confidences(F_orients, orientation_map_rad, args).cpu().numpy()
+        cv2.imwrite(f'{args.orient_dir}/{basename}1.png', indices_cm2)
+        confidence_map = 1 / confidence_map ** 2
+        cv2.imwrite(f'{args.orient_dir}/{basename}_conf.png', confidence_map * 255 / 10)
+        cv2.imwrite(f'{args.orient_dir}/{basename}.png', orientation_map.astype('uint8'))
+        np.save(f'{args.conf_dir}/{basename}.npy', confidence_map.astype('float16'))
 
 
 def calc_confidences(F_orients, orientation_map, args=None, num_filters=180):

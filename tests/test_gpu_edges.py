@@ -126,3 +126,43 @@ def test_gabor_ragged_sizes_vs_oracle(H, W):
     ok = (top2[1] - top2[0]) / res.max() > 1e-4
     assert np.array_equal(orient[0, 0].cpu().numpy()[ok], orient_o.numpy()[ok])
     assert np.abs(conf[0, 0].cpu().numpy() - conf_o.numpy())[ok].max() <= 2e-3
+
+
+def test_shared_reciprocal_division_is_ieee():
+    """mh_div2 (one refined reciprocal for two quotients, mh_common.cuh) against div.rn over 2^28 operand triples:
+    uniform bit patterns inside and outside its fast range, projection-like magnitudes, exact-quotient and
+    near-tie cases, zeros / infinities / NaN / subnormals."""
+    import ctypes as C
+    from monohair_b200._lib import check, lib, ptr, stream_ptr
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(11)
+    bad = torch.zeros((1,), dtype=torch.int64, device=dev)
+    n = 1 << 24
+
+    def run(a0, a1, b):
+        check(lib().mh_debug_div2_check(stream_ptr(dev), ptr(a0.contiguous()), ptr(a1.contiguous()), ptr(b.contiguous()),
+                                        a0.numel(), ptr(bad)), "mh_debug_div2_check")
+
+    def rand_bits():
+        return torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), dtype=torch.int64, device=dev, generator=g).int().view(torch.float32)
+    for _ in range(6):                                     # arbitrary bit patterns (mostly outside the fast range)
+        run(rand_bits(), rand_bits(), rand_bits())
+    for scale in (1.0, 1e-3, 1e3, 1e-9, 1e9, 5e-13, 2e12):  # log-uniform magnitudes around / across the range limits
+        mk = lambda: (torch.exp((torch.rand(n, device=dev, generator=g) - 0.5) * 20) * scale *
+                      torch.sign(torch.rand(n, device=dev, generator=g) - 0.5)).float()
+        run(mk(), mk(), mk())
+    for _ in range(3):                                     # projection-like: pixel-scale numerators over camera depth / offsets
+        z = -(0.4 + torch.rand(n, device=dev, generator=g))
+        run((torch.rand(n, device=dev, generator=g) - 0.5) * 3 * z, (torch.rand(n, device=dev, generator=g) - 0.5) * 3 * z, z)
+        d = (torch.rand(n, device=dev, generator=g) - 0.5) * 40
+        e = (torch.rand(n, device=dev, generator=g) - 0.5) * 40
+        run(d, e, torch.sqrt(d * d + e * e))
+    q = torch.randint(1, 1 << 23, (n,), device=dev, generator=g).float()      # exact quotients and their neighbours
+    b = torch.randint(1, 1 << 12, (n,), device=dev, generator=g).float()
+    run(q * b, torch.nextafter(q * b, torch.full_like(q, 1e30)), b)
+    sp = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 1e-45, -1e-40, 1.17549435e-38, 3.4e38, 1.0, -1.0,
+                       9.094947e-13, 1.0995116e12], device=dev)
+    a0, a1, bb = torch.meshgrid(sp, sp, sp, indexing="ij")
+    run(a0.reshape(-1), a1.reshape(-1), bb.reshape(-1))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0, f"{int(bad.item())} quotients differ from div.rn"

@@ -91,3 +91,84 @@ def test_calc_orientation_maps_f64_vs_oracle():
     d_o = G.difference_of_gaussians(G.rgb2gray(img.astype(np.float64)), 0.4, 10)
     d = MG.difference_of_gaussians(G.rgb2gray(img.astype(np.float64)), 0.4, 10).cpu().numpy()
     assert np.abs(d - d_o).max() <= 1e-12
+
+
+def _line_texture(H, W, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    img = np.zeros((H, W))
+    for _ in range(40):
+        th, lam, ph = rng.uniform(0, np.pi), rng.uniform(3, 6), rng.uniform(0, 2 * np.pi)
+        img += np.cos(2 * np.pi * (xx * np.cos(th) + yy * np.sin(th)) / lam + ph)
+    img = (img - img.min()) / (img.max() - img.min()) * 255
+    return np.clip(img + rng.normal(0, 4, img.shape), 0, 255).astype(np.uint8)
+
+
+def test_calculate_orientation_files_and_batch_generate(tmp_path):
+    """GaborFilter.py:164-237: the three files per image with the reference's encodings: best_ori through
+    cv2.imwrite of a float array (round half to even, saturate: 0.5->0, 1.5->2, 2.5->2), conf through torchvision's
+    save_image (floor(x*255+0.5), three equal channels), Ori as BGR of {1, (sin+1)/2, (cos+1)/2}*255."""
+    import cv2
+    from PIL import Image
+    from monohair_b200 import gabor as GB
+    root = tmp_path
+    (root / "capture_images").mkdir()
+    (root / "hair_mask").mkdir()
+    for i in range(2):
+        Image.fromarray(np.stack([_line_texture(96, 128, 20 + i)] * 3, -1)).save(root / "capture_images" / f"{i:03d}.png")
+        Image.fromarray(np.full((96, 128), 255, np.uint8)).save(root / "hair_mask" / f"{i:03d}.png")
+    GB.batch_generate(str(root), "capture_images")
+    for i in range(2):
+        name = f"{i:03d}.png"
+        image = np.array(Image.open(root / "capture_images" / name).convert('L'))
+        gray = GB.difference_of_gaussians(image, 0.4, 10).type(torch.float)[None, None]
+        ori, best, conf = GB.calOrientationGabor()(gray, None, 1, threshold=0.0)
+        deg = best[0, 0].cpu().numpy().astype(np.float64) / math.pi * 180
+        f_best = cv2.imread(str(root / "best_ori" / name), cv2.IMREAD_UNCHANGED)
+        assert f_best.dtype == np.uint8 and f_best.shape == (96, 128)
+        assert np.array_equal(f_best, np.clip(np.rint(deg), 0, 255).astype(np.uint8))      # np.rint: half to even, like cv2
+        f_conf = np.array(Image.open(root / "conf" / name))
+        c8 = np.floor(conf[0, 0].cpu().numpy().astype(np.float32) * np.float32(255) + np.float32(0.5)).clip(0, 255).astype(np.uint8)
+        assert f_conf.shape == (96, 128, 3) and np.array_equal(f_conf[..., 0], c8) and np.array_equal(f_conf[..., 1], c8)
+        f_ori = cv2.imread(str(root / "Ori" / name), cv2.IMREAD_UNCHANGED)                # BGR as stored
+        o = (ori[0].cpu().numpy().transpose(1, 2, 0).astype(np.float64) + 1) / 2
+        exp = np.concatenate([np.ones((96, 128, 1)), o], axis=2)[..., ::-1] * 255
+        assert np.array_equal(f_ori, np.clip(np.rint(exp), 0, 255).astype(np.uint8))
+        # what PMVO reads back (Load_Ori_And_Conf) decodes to the orientation the bank found, to the 1-degree quantisation
+        back = (180 - f_best.astype(np.float64)) / 180 * math.pi
+        assert np.abs(np.sin(back) - np.sin(math.pi - np.deg2rad(np.rint(deg)))).max() < 1e-12
+    # the encode rules themselves, on exact half-way values
+    probe = np.array([[0.5, 1.5, 2.5, 254.5, 255.5, 300.0, -3.0]], np.float64)
+    cv2.imwrite(str(root / "probe.png"), probe)
+    assert cv2.imread(str(root / "probe.png"), cv2.IMREAD_UNCHANGED).tolist() == [[0, 2, 2, 254, 255, 255, 0]]
+
+
+def test_calc_orientation_maps_main_writes_reference_files(tmp_path):
+    """calc_orientation_maps.py:51-92 end to end on one 64x80 frame: file names, dtypes, and contents equal to the numpy /
+    scipy oracle pushed through the same encodings."""
+    import types
+    import cv2
+    from PIL import Image
+    from monohair_b200 import gabor as GB
+    from oracle import gabor_oracle as G
+    rgb = np.stack([_line_texture(64, 80, 30 + c) for c in range(3)], -1)
+    for d in ("img", "mask"):
+        (tmp_path / d).mkdir()
+    Image.fromarray(rgb).save(tmp_path / "img" / "f0.png")
+    Image.fromarray(np.full((64, 80), 255, np.uint8)).save(tmp_path / "mask" / "f0.png")
+    args = types.SimpleNamespace(img_path=str(tmp_path / "img"), mask_path=str(tmp_path / "mask"), orient_dir=str(tmp_path / "orient"),
+                                 conf_dir=str(tmp_path / "conf"), sigma_x=1.8, sigma_y=2.4, freq=0.23, num_filters=180)
+    GB.main(args)
+    F = G.calc_orients(rgb, G.generate_gabor_filters(1.8, 2.4, 0.23, 180))
+    om = F.argmax(0)
+    idx = cv2.imread(str(tmp_path / "orient" / "f0.png"), cv2.IMREAD_UNCHANGED)
+    assert idx.dtype == np.uint8 and np.array_equal(idx, om.astype('uint8'))
+    conf = np.load(tmp_path / "conf" / "f0.npy")
+    assert conf.dtype == np.float16
+    ref_conf = (1 / G.calc_confidences(F, om / 180 * math.pi) ** 2)
+    assert np.allclose(conf.astype(np.float64), ref_conf.astype(np.float16).astype(np.float64), rtol=2e-3)
+    for f in ("f0_ori.png", "f01.png", "f0_conf.png"):
+        assert (tmp_path / "orient" / f).exists()
+    rad = om / 180 * math.pi
+    cm = (np.stack([np.cos(rad) * 0.5 + 0.5, np.sin(rad) * 0.5 + 0.5, np.zeros_like(rad)], 2).astype(np.float32) * 255)
+    assert np.array_equal(cv2.imread(str(tmp_path / "orient" / "f0_ori.png"), cv2.IMREAD_UNCHANGED), np.clip(np.rint(cm), 0, 255).astype(np.uint8))

@@ -11,6 +11,7 @@ import pytest
 import torch
 from scipy.spatial import KDTree
 
+import gates
 from golden_util import load, scene_of
 
 pytestmark = pytest.mark.gpu
@@ -80,17 +81,8 @@ def test_forward_vs_reference_golden(case):
     # base views: same order as torch.topk on CPU (ties included)
     assert np.array_equal(dbg["base_val"].cpu().numpy(), g["fwd_base_val"])
     assert np.array_equal(dbg["base_idx"].cpu().numpy().astype(np.int64), g["fwd_base_idx"])
-    exact = (loss == g["fwd_loss"]) & np.all(ori == g["fwd_ori"], axis=1)
-    print(f"\nforward: {exact.mean() * 100:.2f}% of {len(loss)} points bit-identical to the reference; "
-          f"max |dloss|={np.abs(loss - g['fwd_loss']).max():.3g} "
-          f"max |dori|={np.abs(ori - g['fwd_ori']).max():.3g}")
-    assert np.abs(loss - g["fwd_loss"]).max() <= LOSS_ATOL
-    assert np.array_equal(hc, g["fwd_hc"])
-    d = np.abs(ori - g["fwd_ori"]).max(axis=1)
-    bad = d > ORI_LINF
-    # a different (equally good within fp noise) depth sample may be picked when two samples' losses tie to ~1e-7
-    assert bad.mean() <= 0.01, f"{bad.sum()} of {len(bad)} directions differ by more than {ORI_LINF}"
-    assert exact.mean() >= 0.95
+    # exact agreement on every point whose decision margin in the oracle exceeds eps; excluded count printed
+    gates.check_forward(g, ori, loss, hc)
 
 
 def test_forward_per_base_losses_vs_oracle(case):
@@ -134,28 +126,17 @@ def test_refine_voxelise_vs_reference_golden(case, tmp_path):
              g["filter_unvisible_in"].copy(), a, infer_inner=False, threshold=float(g["thr"]), genrate_ori_only=False)
     so = np.load(td + "/refine/select_o.npy")
     ml = np.load(td + "/refine/min_loss.npy")
-    print(f"\nrefine: select_o identical rows {np.mean(np.all(so == g['ref_select_o'], 1)) * 100:.2f}%, "
-          f"loss max diff {np.abs(ml - g['ref_min_loss']).max():.3g}")
-    # a near-tie in a kNN medoid can pick another (equally central) neighbour direction, whose re-scored loss differs
-    dml = np.abs(ml - g["ref_min_loss"])
-    assert np.mean(dml <= LOSS_ATOL) >= 0.995 and dml.max() <= 1e-3, (np.mean(dml <= LOSS_ATOL), dml.max())
-    assert np.mean(np.all(so == g["ref_select_o"], 1)) >= 0.98
+    clean, sel_certain = gates.check_refine(g, so, ml)
     fu_p = np.load(td + "/refine/filter_unvisible.npy")
     fu_o = np.load(td + "/refine/filter_unvisible_ori.npy")
-    assert np.array_equal(fu_p, g["ref_fu_points"])                    # head filter decisions: exact
-    assert np.mean(np.all(fu_o == g["ref_fu_ori"], 1)) >= 0.98
+    gates.check_near_surface(g, fu_p, fu_o, sel_certain)
     Occ = scipy.io.loadmat(td + "/refine/Occ3D.mat")["Occ"]
     Ori = scipy.io.loadmat(td + "/refine/Ori3D.mat")["Ori"]
     assert Occ.dtype == np.float64 and Ori.dtype == np.float64
     assert tuple(Ori.shape) == tuple(g["mat_ori_shape"])
-    nz = np.argwhere(Occ > 0)
-    assert np.array_equal(nz, g["mat_occ_nz"])                         # occupancy: bit-exact
     Z = Occ.shape[2]
-    vals = np.stack([Ori[i, j, [k, k + Z, k + 2 * Z]] for i, j, k in nz])
-    same = np.all(vals == g["mat_ori_nz"], axis=1)
-    print(f"orientation volume: {same.mean() * 100:.2f}% of {len(nz)} occupied voxels bit-identical; "
-          f"L-inf over the rest {np.abs(vals - g['mat_ori_nz'])[~same].max() if (~same).any() else 0:.3g}")
-    assert same.mean() >= 0.97
+    gates.check_volume(g, Occ, Ori, True if clean.all() else np.concatenate([clean[ml < float(g["thr"])], np.ones(len(fu_p), bool)]),
+                       sel_certain)
     assert np.all(Ori.reshape(Occ.shape[0], Occ.shape[1], 3, Z).transpose(0, 1, 3, 2)[Occ == 0] == 0)
 
 
