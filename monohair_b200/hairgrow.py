@@ -199,9 +199,18 @@ class HairGrowing:
 
     def VoxelToWorld(self, strands, bust_to_origin=None):
         """HairGrow.py:816-824."""
+        if len(strands) == 0:
+            return []
+        if torch.is_tensor(strands[0]):
+            # all strands through ONE transform and ONE device->host copy (the reference converts strand by strand)
+            sizes = [int(s.shape[0]) for s in strands]
+            allp = voxel_to_points(torch.cat(strands, 0)).cpu().numpy()
+            if bust_to_origin is not None:
+                allp -= np.asarray(bust_to_origin)          # float64 operand, rounded into the float32 array like the reference's ss -= ...
+            return np.split(allp, np.cumsum(sizes)[:-1])
         out = []
         for ss in strands:
-            ss = voxel_to_points(ss).cpu().numpy()
+            ss = voxel_to_points(torch.as_tensor(ss)).cpu().numpy()
             if bust_to_origin is not None:
                 ss -= bust_to_origin
             out.append(ss)
