@@ -384,7 +384,9 @@ def run_b200(args, cfg):
     # ---- the other BASELINE configs (rank 0, N=1, outside the timed region) -------------------------------------
     other = None
     if rank == 0 and world == 1 and not args.no_extra:
+        import contextlib
         try:
+          with contextlib.redirect_stdout(sys.stderr):            # stdout carries the one JSON line only
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_extra
             torch.cuda.empty_cache()

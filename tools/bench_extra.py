@@ -78,7 +78,7 @@ def bench_gabor():
         print(json.dumps({k: v}))
 
 
-def hairgrow_workload(cpu=True, shell_mm=6.0, tmpdir=None):
+def hairgrow_workload(cpu=True, shell_mm=6.0, tmpdir=None, n_roots=90000):
     """BASELINE configs[3]: strands through a 256x256x192 orientation field; the shell is thick enough for >= 100 k
     accepted strands.  Also times the stage end to end from the .mat pair to scalp_segment.hair."""
     import tempfile
@@ -96,7 +96,7 @@ def hairgrow_workload(cpu=True, shell_mm=6.0, tmpdir=None):
     hg = HairGrowing(volume=vol, device="cuda:0")
     # scalp roots on a smaller ellipsoid, voxel coordinates
     rng = np.random.default_rng(0)
-    d = rng.normal(size=(200000, 3)); d /= np.linalg.norm(d, axis=-1, keepdims=True); d = d[d[:, 1] > 0.2][:60000]
+    d = rng.normal(size=(400000, 3)); d /= np.linalg.norm(d, axis=-1, keepdims=True); d = d[d[:, 1] > 0.2][:n_roots]
     r = np.array(syn.RADII) * 0.9
     p = d * r
     nrm = p / (r * r); nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
@@ -123,7 +123,7 @@ def hairgrow_workload(cpu=True, shell_mm=6.0, tmpdir=None):
     hg._accept(rp, ro, rl, None, flag0, 1)
     ms_accept = ev_time(lambda: hg._accept(pts_a, off_a, ln_a, seeds, flag0.clone(), 0), reps=3, warm=1)
     out = {"config": "HairGrow GenerateGuideStrandFromScalp, 256x256x192 volume (BASELINE configs[3])",
-           "occupied_voxels": M, "seeds": int(60000 + 2 * M), "strands": len(strands), "num_root": num_root, "points": n_pts,
+           "occupied_voxels": M, "seeds": int(n_roots + 2 * M), "strands": len(strands), "num_root": num_root, "points": n_pts,
            "s_total": dt, "strands_per_s": len(strands) / dt, "trace_only_ms_per_pass": ms_trace,
            "trace_seeds_per_s": M / (ms_trace * 1e-3), "trace_steps_per_pass": steps,
            # one dependent 16 B voxel fetch + 12 B point write per step: a latency / random-sector kernel, not a streaming one
