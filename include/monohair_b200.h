@@ -233,6 +233,16 @@ int64_t mh_gabor_workspace_bytes(int32_t H, int32_t W, int32_t n_filters);
 int mh_gabor_orientation(void* stream, const float* image, int32_t H, int32_t W, const float* bank, int32_t n_filters,
                          int32_t ksize, float clamp_low, float clamp_high, float* orient, float* conf,
                          float* two_channel, void* workspace, int64_t workspace_bytes);
+/* The same result on the tensor cores (tcgen05.mma kind::tf32 with a 3-term hi/lo split for fp32 accuracy, fp32
+ * accumulators in TMEM, bank streamed by TMA bulk copies), with the per-pixel epilogue fused: the 180 responses of a
+ * pixel never leave the chip.  bank_tc: the 180 x 17 x 17 bank pre-split and pre-laid-out by the host
+ * (mh_gabor_tc_bank_bytes() bytes: [17 kernel rows][hi, lo][6 k-groups][24 filter groups][8][4] float32, zero padded).
+ * workspace: H*W floats + 256 B.  Orientation indices agree with mh_gabor_orientation wherever the top-2 response margin
+ * exceeds ~1e-6 of the largest response. */
+int64_t mh_gabor_tc_bank_bytes(void);
+int mh_gabor_orientation_tc(void* stream, const float* image, int32_t H, int32_t W, const void* bank_tc, int32_t n_filters,
+                            float clamp_low, float clamp_high, float* orient, float* conf, float* two_channel,
+                            void* workspace, int64_t workspace_bytes);
 /* Generic filter-bank responses in float64 with periodic ('wrap') true convolution: calc_orients
  * (calc_orientation_maps.py:27-32).  bank [n][k][k] zero-padded to k x k; out |response| [n][H][W]. */
 int mh_filterbank_wrap_f64(void* stream, const double* image, int32_t H, int32_t W, const double* bank,

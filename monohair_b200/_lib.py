@@ -75,6 +75,8 @@ _SIGS = {
     "mh_smooth_strands": (C.c_int, [p, p, p, p, i64, f64, f64, p, p, i64, i64]),
     "mh_gabor_workspace_bytes": (i64, [i32, i32, i32]),
     "mh_gabor_orientation": (C.c_int, [p, p, i32, i32, p, i32, i32, f32, f32, p, p, p, p, i64]),
+    "mh_gabor_tc_bank_bytes": (i64, []),
+    "mh_gabor_orientation_tc": (C.c_int, [p, p, i32, i32, p, i32, f32, f32, p, p, p, p, i64]),
     "mh_filterbank_wrap_f64": (C.c_int, [p, p, i32, i32, p, i32, i32, p]),
     "mh_dog_f64": (C.c_int, [p, p, i32, i32, p, i32, p, i32, p, p]),
     "mh_debug_topk_host": (C.c_int, [p, i32, i32, p, p]),

@@ -194,6 +194,13 @@ __global__ void sub_kernel(const double* a, const double* b, int64_t n, double* 
 
 }  // namespace
 
+// shared with gabor_tc.cu
+void gabor_finish_launch(cudaStream_t st, int64_t HW, const float* orient, const float* var, const unsigned int* gmax, float lo,
+                         float hi, float* conf, float* two) {
+    gabor_finish_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, st>>>(HW, orient, var, gmax, lo, hi, conf, two);
+    MH_COUNT_LAUNCH();
+}
+
 // workspace: [resp nf*H*W floats][var H*W floats][gmax 64 B]
 extern "C" int64_t mh_gabor_workspace_bytes(int32_t H, int32_t W, int32_t nf) {
     return (int64_t)4 * ((int64_t)nf * H * W + (int64_t)H * W) + 256;

@@ -14,12 +14,38 @@ import torch.nn as nn
 from ._lib import check, lib, ptr, stream_ptr
 
 
+def bank_for_tensor_cores(bank):
+    """[n<=192,17,17] float32 bank -> the operand mh_gabor_orientation_tc streams: per kernel row r the matrix
+    B_r[filter][tap] (192 x 24, zero padded) split into tf32 parts hi = rna(x), lo = rna(x - hi) (round to nearest, ties
+    away: what cvt.rna.tf32.f32 does to the image operand on the device) and laid out as the tensor core reads it from
+    shared memory: [k-group of 4 taps][group of 8 filters][8 filters][4 taps]."""
+    b = np.asarray(bank, dtype=np.float32)
+    n, ks, _ = b.shape
+    assert ks == 17 and n <= 192
+
+    def rna(x):
+        u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+        return ((u + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
+    out = np.zeros((17, 2, 6, 24, 8, 4), dtype=np.float32)
+    full = np.zeros((17, 192, 24), dtype=np.float32)
+    full[:, :n, :17] = b.transpose(1, 0, 2)                     # [r][filter][tap]
+    hi = rna(full)
+    lo = rna(full - hi)
+    for part, m in enumerate((hi, lo)):
+        out[:, part] = m.reshape(17, 24, 8, 6, 4).transpose(0, 3, 1, 2, 4)     # [r][ng][nr][kg][ke] -> [r][kg][ng][nr][ke]
+    return out
+
+
 class calOrientationGabor(nn.Module):
     """GaborFilter.py:16-145.  forward() keeps the reference signature; only iter=1 (the only value the pipeline
-    uses, GaborFilter.py:237) is implemented on the device."""
+    uses, GaborFilter.py:237) is implemented on the device.  Two kernels: the tensor-core one (tcgen05, 3-term tf32 split,
+    fused epilogue; default) and the fp32 CUDA-core one that reproduces the reference's arg-max on every pixel of the
+    goldens (tensor_cores=False, or MH_GABOR_FP32=1)."""
 
-    def __init__(self, channel_in=1, channel_out=1, stride=1):
+    def __init__(self, channel_in=1, channel_out=1, stride=1, tensor_cores=None):
         super().__init__()
+        self.tensor_cores = (os.environ.get("MH_GABOR_FP32", "0") != "1") if tensor_cores is None else bool(tensor_cores)
+        self._bank_tc = None
         self.channel_in = channel_in
         self.channel_out = channel_out
         self.numKernels = 180
@@ -66,6 +92,18 @@ class calOrientationGabor(nn.Module):
         orient = torch.empty((1, 1, H, W), dtype=torch.float32, device=dev)
         conf = torch.empty((1, 1, H, W), dtype=torch.float32, device=dev)
         two = torch.empty((1, 2, H, W), dtype=torch.float32, device=dev)
+        if self.tensor_cores:
+            if self._bank_tc is None or self._bank_tc.device != dev:
+                self._bank_tc = torch.from_numpy(bank_for_tensor_cores(bank.cpu().numpy())).to(dev).contiguous()
+                assert self._bank_tc.numel() * 4 == lib().mh_gabor_tc_bank_bytes()
+            wsb = 4 * H * W + 256
+            ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                check(lib().mh_gabor_orientation_tc(stream_ptr(dev), ptr(img), H, W, ptr(self._bank_tc), self.numKernels,
+                                                    float(self.clamp_confidence_low), float(self.clamp_confidence_high),
+                                                    ptr(orient), ptr(conf), ptr(two), ptr(ws), wsb), "mh_gabor_orientation_tc")
+            conf[conf < threshold] = 0
+            return two, orient, conf
         wsb = lib().mh_gabor_workspace_bytes(H, W, self.numKernels)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):

@@ -22,12 +22,15 @@ def test_bank_matches_reference():
     assert np.array_equal(calOrientationGabor().bank("cuda:0").cpu().numpy(), g["bank"])
 
 
-def test_gabor_orientation_vs_reference_golden():
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fp32_cuda_cores", "tcgen05_tf32x3"])
+def test_gabor_orientation_vs_reference_golden(tensor_cores):
+    """both kernels against the unmodified reference (CPU, fp32): the CUDA-core one and the tensor-core one (tcgen05,
+    3-term tf32 split, fused epilogue); same margin gate, same tolerances."""
     from monohair_b200.gabor import calOrientationGabor
     from oracle import gabor_oracle as G
     g = load("gabor_small")
     img = torch.from_numpy(g["image"])[None, None].cuda()
-    two, orient, conf = calOrientationGabor()(img, None, iter=1, threshold=0.0)
+    two, orient, conf = calOrientationGabor(tensor_cores=tensor_cores)(img, None, iter=1, threshold=0.0)
     orient, conf, two = orient[0, 0].cpu().numpy(), conf[0, 0].cpu().numpy(), two[0].cpu().numpy()
     _, _, _, res = G.gabor_orientation(g["image"])
     res = res.numpy()
@@ -45,7 +48,8 @@ def test_gabor_orientation_vs_reference_golden():
     assert set(np.unique(orient)) <= set(np.unique(g["orient"])) | {np.float32(0)}
 
 
-def test_full_frame_properties():
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fp32_cuda_cores", "tcgen05_tf32x3"])
+def test_full_frame_properties(tensor_cores):
     """1080p frame: a pure sinusoidal grating must come back with its own orientation (up to the bank's 1 degree),
     confidence in [0,1], and the result must not depend on the tile decomposition (shifted crop equality)."""
     from monohair_b200.gabor import calOrientationGabor
@@ -53,7 +57,7 @@ def test_full_frame_properties():
     yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
     th = math.radians(30.0)
     img = (0.1 * torch.cos(2 * math.pi * (yy * math.cos(th) + xx * math.sin(th)) / 4.0)).float()
-    m = calOrientationGabor()
+    m = calOrientationGabor(tensor_cores=tensor_cores)
     two, orient, conf = m(img[None, None].cuda())
     o = orient[0, 0, 100:-100, 100:-100]
     assert float(conf.min()) >= 0 and float(conf.max()) <= 1
@@ -172,3 +176,22 @@ def test_calc_orientation_maps_main_writes_reference_files(tmp_path):
     rad = om / 180 * math.pi
     cm = (np.stack([np.cos(rad) * 0.5 + 0.5, np.sin(rad) * 0.5 + 0.5, np.zeros_like(rad)], 2).astype(np.float32) * 255)
     assert np.array_equal(cv2.imread(str(tmp_path / "orient" / "f0_ori.png"), cv2.IMREAD_UNCHANGED), np.clip(np.rint(cm), 0, 255).astype(np.uint8))
+
+
+def test_tensor_core_bank_agrees_with_fp32_bank_on_ragged_sizes():
+    """tcgen05 kernel vs the CUDA-core kernel on sizes that are not multiples of its 128 x 2 tile (edges, odd heights):
+    orientation identical wherever the fp32 kernel's top-2 margin is above 1e-5 of the largest response."""
+    from monohair_b200.gabor import calOrientationGabor
+    from oracle import gabor_oracle as G
+    for (H, W), seed in (((33, 129), 1), ((2, 128), 2), ((65, 40), 3), ((131, 300), 4)):
+        img = _line_texture(H, W, seed).astype(np.float32) / 255.0 - 0.5
+        x = torch.from_numpy(img)[None, None].cuda()
+        _, o_ref, c_ref = calOrientationGabor(tensor_cores=False)(x)
+        _, o_tc, c_tc = calOrientationGabor(tensor_cores=True)(x)
+        _, _, _, res = G.gabor_orientation(img)
+        res = res.numpy()
+        top2 = np.sort(res, axis=0)[-2:]
+        ok = torch.from_numpy((top2[1] - top2[0]) / res.max() > 1e-5).cuda()
+        assert ok.float().mean() > 0.5
+        assert torch.equal(o_tc[0, 0][ok], o_ref[0, 0][ok]), (H, W)
+        assert float((c_tc - c_ref)[0, 0][ok].abs().max()) <= 2e-3
