@@ -4,8 +4,10 @@ closer to flipping than the eps below; excluded items are counted and printed, a
 
 The kernels follow the reference's fp32 operation order, so the eps are a few ulps of the compared quantity, not
 "percent of items allowed to differ":
-  EPS_FWD   2e-8  winning vs runner-up (base view, depth sample) loss; losses are ~1e-2..1, one ulp there is <= 6e-8,
-                  the one known order deviation (torch.sum's interleaved tail columns) moves a loss by <= 1 ulp
+  EPS_FWD   5e-8  winning vs runner-up (base view, depth sample) loss; a loss is sum(l*w)/sum(w) with sums of a few units,
+                  and the one known order deviation (torch.sum's interleaved tail columns) moves either sum by
+                  an ulp: <= ~1e-8 on a loss (largest deviation seen at BASELINE scale: 9.4e-9), so two candidate losses
+                  closer than 5e-8 may legitimately swap (2.6 % of the items at BASELINE scale)
   EPS_KNN   1e-13 gap between consecutive neighbour distances (float64, ~1e-3 m): set membership and summation order
   EPS_UPD   2e-7  | |cos(center, ori)| - 0.95 |, the update threshold of refine step (i)
   EPS_SEL   2e-8  | refine loss - threshold |, membership of the selected set
@@ -15,7 +17,7 @@ certain; the number of medoids whose top-2 gap is below 1e-6 is printed to show 
 """
 import numpy as np
 
-EPS_FWD, EPS_KNN, EPS_UPD, EPS_SEL, EPS_ROUND = 2e-8, 1e-13, 2e-7, 2e-8, 1e-9
+EPS_FWD, EPS_KNN, EPS_UPD, EPS_SEL, EPS_ROUND = 5e-8, 1e-13, 2e-7, 2e-8, 1e-9
 MAX_EXCLUDED = 0.05
 
 
@@ -33,7 +35,7 @@ def check_forward(g, ori, loss, hc, what="forward"):
           f"directions bit-identical, max|dloss| {dl[keep].max():.3g}; excluded set: {exact[~keep].mean() * 100 if ex else 100:.1f}% identical")
     assert ex <= MAX_EXCLUDED * n, f"{ex} of {n} items excluded by the margin gate"
     assert exact[keep].all(), f"{int((~exact[keep]).sum())} directions differ on items with margin > {EPS_FWD:g}"
-    assert dl[keep].max() <= EPS_FWD
+    assert dl[keep].max() <= 2e-8
     assert np.array_equal(hc[keep], g["fwd_hc"][keep])
     assert dl.max() <= 1e-5                                        # every item: the loss itself never moves by more
 
