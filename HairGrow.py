@@ -9,7 +9,8 @@ import numpy as np
 import torch
 
 from monohair_b200 import options
-from monohair_b200.hairgrow import HairGrowing, points_to_voxel, save_hair_strands, smooth_strands, voxel_to_points  # noqa: F401
+from monohair_b200.hairgrow import (HairGrowing, load_strand, points_to_voxel, save_hair_strands, smooth_strands,  # noqa: F401
+                                    voxel_to_points)
 from monohair_b200.pmvo_utils import read_obj, read_obj_normals, sample_points_uniformly  # noqa: F401
 
 
@@ -53,9 +54,38 @@ def main():
         strands = smooth_strands(strands, 4.0, 2.0, device=args.device)                       # HairGrow.py:914-916
         save_hair_strands(os.path.join(args.save_path, 'scalp_segment_smooth.hair'), strands)
         np.save(args.save_path + '/num_root.npy', np.array(num_root))
-    if args.HairGenerate.connect_segments or args.HairGenerate.connect_scalp:
-        print('connect_segments / connect_scalp are outside the B200 hot path (SURVEY.md §8f); '
-              'run the reference HairGrow.py with --HairGenerate.generate_segments! on the files written here.')
+    else:
+        num_root = int(np.load(args.save_path + '/num_root.npy'))
+    if args.HairGenerate.connect_segments:                                                      # HairGrow.py:925-950
+        segment, points = load_strand(os.path.join(args.save_path, 'scalp_segment.hair'))
+        strands, beg = [], 0
+        for i, seg in enumerate(segment):
+            strand = points[beg:beg + seg]
+            if i >= num_root:
+                strand += args.bust_to_origin
+            strands.append(strand)
+            beg += seg
+        solver.strands = strands
+        connected = solver.find_connect_info(strands[num_root:], args.HairGenerate.connect_threshold,
+                                             args.HairGenerate.connect_dot_threshold, solver.occ)
+        new_strands = strands[:num_root] + [ss - args.bust_to_origin for ss in connected]
+        new_strands = smooth_strands(new_strands, 4.0, 2.0, device=args.device)
+        save_hair_strands(os.path.join(args.save_path, 'strands.hair'), new_strands)
+    if args.HairGenerate.connect_scalp:                                                         # HairGrow.py:952-976
+        segment, points = load_strand(os.path.join(args.save_path, 'strands.hair'))
+        strands, beg = [], 0
+        for seg in segment:
+            strands.append(points[beg:beg + seg])
+            beg += seg
+        strands = solver.WorldToVoxel(strands, args.bust_to_origin)
+        connect_strands = solver.connect_to_scalp(strands, num_root, args.HairGenerate.out_ratio, bool(args.PMVO.infer_inner))
+        out = []
+        for ss in connect_strands:
+            ss = voxel_to_points(torch.from_numpy(ss.copy())).cpu().numpy()
+            ss -= args.bust_to_origin
+            out.append(ss)
+        out = smooth_strands(out, 4.0, 2.0, device=args.device)
+        save_hair_strands(os.path.join(args.save_path, 'connected_strands.hair'), out)
 
 
 if __name__ == '__main__':

@@ -218,6 +218,24 @@ int mh_accept_strands(void* stream, const float* points, const int64_t* offsets,
                       const float* seeds, int64_t n, int32_t gx, int32_t gy, int32_t gz, int32_t mode,
                       float* flag, uint8_t* accepted);
 
+/* ---- HairGrow connect stage (HairGrowing.find_connect_info, HairGrow.py:436-505, :548-584) ------------------------- */
+/* For every strand (float64 points[offsets[i] .. +lengths[i]), world frame, metres) and each of its two ends: the partner
+ * strand the reference would connect it to.  End-point candidates: the 50 nearest end points strictly within
+ * connect_threshold, roots first and tips only if the roots give nothing (query + find_best_connect_strands); per
+ * candidate the orientation test against dot_threshold, the strand-to-strand proximity rules of :565-578 and the loss
+ * distance * (1 - |cos|), first minimum.  info int32 [n][4] = {root partner, its end, tip partner, its end}, partner -1 /
+ * end 0 = none, end 1 = the partner's root, 2 = its tip.  *overflow is set when more than 256 end points fall inside one
+ * query radius (the result would not be exact). */
+int mh_connect_find(void* stream, const double* points, const int64_t* offsets, const int32_t* lengths, int64_t n_strands,
+                    double connect_threshold, double dot_threshold, int32_t* info, int32_t* overflow);
+/* Share of each strand's points on occupied voxels as HairGrow.py:514-523 evaluates it (points_to_voxel with the float32
+ * voxel_min, torch.round, negative-index wrap), -1 when an index leaves the grid upwards.  shift (optional float64 [n][3]) is
+ * added to every point of strand i first (the random perturbation of :531); voxel_space != 0: points are voxel coordinates
+ * already (random_move_strands, PMVO_utils.py:629). */
+int mh_strand_occupancy(void* stream, const double* points, const int64_t* offsets, const int32_t* lengths, int64_t n_strands,
+                        const double* shift, const void* volume, int32_t gx, int32_t gy, int32_t gz, int32_t voxel_space,
+                        double* frac);
+
 /* ---- strand smoothing (Utils/Utils.py:1148-1198 smnooth_strand / smooth_strands; HairGrow.py:914, :950, :975) ---- */
 /* Per strand (points[offsets[i] .. +lengths[i])) and axis: least squares of [lap*L ; pos*I] x = [0 ; pos*s] with L the
  * second-difference operator (first differences at the ends), solved in float64 through the pentadiagonal normal

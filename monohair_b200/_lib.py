@@ -71,6 +71,8 @@ _SIGS = {
     "mh_trace_write": (C.c_int, [p, p, i32, i32, i32, p, i64, f32, i32, p, p, p, i32, p]),
     "mh_trace_from_scalp": (C.c_int, [p, p, i32, i32, i32, p, p, i64, f32, i32, i32, p, p]),
     "mh_accept_strands": (C.c_int, [p, p, p, p, p, i64, i32, i32, i32, i32, p, p]),
+    "mh_connect_find": (C.c_int, [p, p, p, p, i64, f64, f64, p, p]),
+    "mh_strand_occupancy": (C.c_int, [p, p, p, p, i64, p, p, i32, i32, i32, i32, p]),
     "mh_smooth_strands_workspace_bytes": (i64, [i64]),
     "mh_smooth_strands": (C.c_int, [p, p, p, p, i64, f64, f64, p, p, i64, i64]),
     "mh_gabor_workspace_bytes": (i64, [i32, i32, i32]),

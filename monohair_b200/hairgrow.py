@@ -197,6 +197,26 @@ class HairGrowing:
                                          seedNormal.to(self.device).type(torch.float).reshape(1, 3).contiguous(), thrDot)
         return None if int(ln[0]) == 0 else pts[: int(ln[0])]
 
+    # ------------------------------------------------------------------ connect stages (monohair_b200/hairgrow_connect.py)
+    def find_connect_info(self, strands, connect_threshold=0.005, connect_dot_threshold=0.7, occ=None):
+        """HairGrow.py:436-546 (the `occ` argument of the reference is this solver's own volume)."""
+        from . import hairgrow_connect as HC
+        return HC.find_connect_info(strands, connect_threshold, connect_dot_threshold, self.volume, self.device)
+
+    def connect_segments(self, strands_connect_info, strands, i):
+        """HairGrow.py:303-346 with the connection table of mh_connect_find (int32 [n,4])."""
+        from . import hairgrow_connect as HC
+        return HC.connect_segments(strands_connect_info, strands, i)
+
+    def connect_strands(self, strand1, strand2, push_back, cubic_sample=False, add_mid=True, need_weight=False):
+        from . import hairgrow_connect as HC
+        return HC.connect_strands(strand1, strand2, push_back, cubic_sample, add_mid, need_weight)
+
+    def connect_to_scalp(self, strands, num_root, out_ratio=0.5, infer_inner=True):
+        """HairGrow.py:606-784 (out_ratio = args.HairGenerate.out_ratio, a module global in the reference)."""
+        from . import hairgrow_connect as HC
+        return HC.connect_to_scalp(strands, num_root, self.volume, out_ratio, infer_inner)
+
     def VoxelToWorld(self, strands, bust_to_origin=None):
         """HairGrow.py:816-824."""
         if len(strands) == 0:

@@ -34,8 +34,9 @@ PMVO:
   infer_inner:
 HairGenerate:
   grow_threshold: 0.85
-  connect_segments:
-  connect_scalp:
+  connect_threshold: 0.0025
+  connect_dot_threshold: 0.8
+  out_ratio: 0.35
 """)
     env = dict(os.environ, PYTHONPATH=ROOT)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "PMVO.py"), f"--yaml={cfgdir}/synth"], cwd=ROOT, env=env,
@@ -75,3 +76,12 @@ HairGenerate:
     # strands live near the shell (world frame, bust offset removed again by VoxelToWorld)
     k = np.linalg.norm((pts + np.array([0.006, -1.644, 0.010])) / np.array(syn.RADII), axis=1)
     assert np.percentile(np.abs(k - 1), 90) < 0.25
+    # connect stages (HairGrow.py:925-976): strands.hair keeps every strand (segments possibly extended through their partners),
+    # connected_strands.hair keeps the rooted ones
+    seg_c, pts_c = load_strand(str(out / "refine/strands.hair"))
+    assert len(seg_c) == len(seg) and list(seg_c[:num_root]) == list(seg[:num_root])
+    assert all(a >= b for a, b in zip(seg_c, seg)) and sum(seg_c) >= sum(seg)
+    seg_f, pts_f = load_strand(str(out / "refine/connected_strands.hair"))
+    assert num_root <= len(seg_f) <= len(seg_c) and pts_f.shape == (sum(seg_f), 3) and np.isfinite(pts_f).all()
+    k = np.linalg.norm((pts_f + np.array([0.006, -1.644, 0.010])) / np.array(syn.RADII), axis=1)
+    assert np.percentile(np.abs(k - 1), 90) < 0.3
