@@ -51,7 +51,7 @@ def main():
         points = None
         if rank == 0:
             points = load_colmap_points(args.data.raw_points_path, args.bbox_min, args.bust_to_origin, 0.005 / 4,
-                                        [512, 512, 384], True, args.PMVO.num_sample_per_grid)
+                                        [512, 512, 384], True, args.PMVO.num_sample_per_grid, device=args.device)
         points = _impl.broadcast_array(points, args.device)
         raw_points = points.copy()
         print('total points:', points.shape[0])

@@ -218,6 +218,24 @@ int mh_accept_strands(void* stream, const float* points, const int64_t* offsets,
                       const float* seeds, int64_t n, int32_t gx, int32_t gy, int32_t gz, int32_t mode,
                       float* flag, uint8_t* accepted);
 
+/* ---- candidate sampling (SamplePointsAroundmesh, Utils/PMVO_utils.py:316-339) ---------------------------------------- */
+/* occ uint8 [gx][gy][gz] = 1 on the cell of every surface sample (y, z negated, float64 round half to even, clipped). */
+int mh_sample_mark_cells(void* stream, const double* points /*[n][3]*/, int64_t n, const double* bbox_min_host, double vsize,
+                         int32_t gx, int32_t gy, int32_t gz, uint8_t* occ);
+/* out float64 [m*num_per_grid][3]: (cell + rnd) * vsize + bbox_min with y, z negated; cells int64 [m][3] in np.nonzero
+ * order, tiled num_per_grid times; rnd float64 [m*num_per_grid][3] = the reference's np.random.random draws. */
+int mh_sample_cells(void* stream, const int64_t* cells, int64_t m, int32_t num_per_grid, const double* rnd,
+                    const double* bbox_min_host, double vsize, double* out);
+
+/* ---- depth-map producer (render_bust_hair_depth, Utils/Render_utils.py:310-347; shaders :150-178) -------------------- */
+/* Rasterises a triangle mesh (verts float32 [n][3] world frame, faces int32 [m][3]) as the reference's OpenGL pass does:
+ * depth [H][W] = -z_cam / 2 of the nearest fragment (perspective-correct), 1 where nothing is drawn, row 0 on top, in the
+ * pixel mapping of PMVO.project_points.  cam_record_host: mh_views_pack_camera_host record.  clear = 0 draws on top of the
+ * meshes already in zbuf (the reference adds the bust to the same frame).  The reference needs moderngl + EGL, absent
+ * here: this stage is restated, not pinned (oracle/render_oracle.py). */
+int mh_render_depth(void* stream, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces,
+                    const float* cam_record_host, int32_t H, int32_t W, float* depth, void* zbuf, int32_t clear);
+
 /* ---- HairGrow connect stage (HairGrowing.find_connect_info, HairGrow.py:436-505, :548-584) ------------------------- */
 /* For every strand (float64 points[offsets[i] .. +lengths[i]), world frame, metres) and each of its two ends: the partner
  * strand the reference would connect it to.  End-point candidates: the 50 nearest end points strictly within

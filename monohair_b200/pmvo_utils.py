@@ -144,8 +144,31 @@ def sample_points_uniformly(vertices, faces, number_of_points, rng=None, with_no
     return pts
 
 
-def SamplePointsAroundmesh(colmap_points, bbox_min, vsize, num_per_grid=32, grid_resolution=[512, 512, 384]):
-    """PMVO_utils.py:316-339 (np.random.random, seeded through options.process_options)."""
+def SamplePointsAroundmesh(colmap_points, bbox_min, vsize, num_per_grid=32, grid_resolution=[512, 512, 384], device=None):
+    """PMVO_utils.py:316-339 (np.random.random, seeded through options.process_options).  With a CUDA `device` the cell
+    marking, the compaction in np.nonzero order and the sample arithmetic run on the device (csrc/sample.cu, float64, the
+    reference's operation order); the random numbers are still drawn from numpy's global stream on the host, in the same
+    shape and order, so the result is bit-identical to the host path.  Like the reference, flips colmap_points in place."""
+    if device is not None and torch.device(device).type == "cuda":
+        import ctypes as C
+        from ._lib import check, lib, ptr, stream_ptr
+        dev = torch.device(device)
+        gx, gy, gz = [int(g) for g in grid_resolution]
+        pts = torch.from_numpy(np.ascontiguousarray(colmap_points, dtype=np.float64)).to(dev)
+        colmap_points[:, 1:] *= -1                                 # the in-place flip the caller observes (:318)
+        bmin = np.ascontiguousarray(np.asarray(bbox_min, dtype=np.float64))
+        occ = torch.empty((gx, gy, gz), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mh_sample_mark_cells(stream_ptr(dev), ptr(pts), pts.size(0), bmin.ctypes.data_as(C.c_void_p), float(vsize),
+                                             gx, gy, gz, ptr(occ)), "mh_sample_mark_cells")
+        cells = torch.nonzero(occ).contiguous()                    # lexicographic (x, y, z), like np.nonzero
+        m = int(cells.size(0))
+        rnd = torch.from_numpy(np.random.random((m * num_per_grid, 3))).to(dev)
+        out = torch.empty((m * num_per_grid, 3), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mh_sample_cells(stream_ptr(dev), ptr(cells), m, int(num_per_grid), ptr(rnd), bmin.ctypes.data_as(C.c_void_p),
+                                        float(vsize), ptr(out)), "mh_sample_cells")
+        return out.cpu().numpy()
     occ = np.zeros(grid_resolution, dtype=bool)
     colmap_points[:, 1:] *= -1
     indexs = np.round((colmap_points - bbox_min) / vsize).astype(np.int32)
@@ -161,15 +184,16 @@ def SamplePointsAroundmesh(colmap_points, bbox_min, vsize, num_per_grid=32, grid
     return sample
 
 
-def load_colmap_points(path, bbox_min, bust_to_origin, vsize=0.005, grid_resolution=[128, 128, 96], sample=True, num_per_grid=8):
-    """PMVO_utils.py:341-362."""
+def load_colmap_points(path, bbox_min, bust_to_origin, vsize=0.005, grid_resolution=[128, 128, 96], sample=True, num_per_grid=8,
+                       device=None):
+    """PMVO_utils.py:341-362 (`device`: run the cell sampling on that CUDA device)."""
     v, f = read_obj(path)
     print('num_p:', v.shape[0])
     colmap_points = sample_points_uniformly(v, f, v.shape[0] * 5)
     colmap_points += bust_to_origin
     if sample:
         sample_points = SamplePointsAroundmesh(colmap_points.copy(), bbox_min, vsize, num_per_grid=num_per_grid,
-                                               grid_resolution=grid_resolution)
+                                               grid_resolution=grid_resolution, device=device)
         print('num sample:', sample_points.shape[:])
         return sample_points
     return colmap_points

@@ -166,3 +166,65 @@ def test_shared_reciprocal_division_is_ieee():
     run(a0.reshape(-1), a1.reshape(-1), bb.reshape(-1))
     torch.cuda.synchronize()
     assert int(bad.item()) == 0, f"{int(bad.item())} quotients differ from div.rn"
+
+
+def test_candidate_sampling_on_device_equals_host_path():
+    """SamplePointsAroundmesh (PMVO_utils.py:316-339): the device path (cell marking, np.nonzero-order compaction, float64
+    sample arithmetic; random numbers from numpy's seeded global stream) is bit-identical to the numpy path, including
+    points exactly on .5 cell boundaries and outside the grid."""
+    from monohair_b200.pmvo_utils import SamplePointsAroundmesh
+    rng = np.random.default_rng(3)
+    pts = (rng.normal(size=(30000, 3)) * np.array([0.1, 0.13, 0.11]))
+    bmin, vs = np.array([-0.32, -0.32, -0.24]), 0.005 / 4
+    pts[:50] = np.round(pts[:50] / vs) * vs + vs / 2            # rounding boundaries
+    pts[50:60] *= 10                                             # clipped
+    np.random.seed(7)
+    a = SamplePointsAroundmesh(pts.copy(), bmin, vs, num_per_grid=4, grid_resolution=[512, 512, 384])
+    np.random.seed(7)
+    p2 = pts.copy()
+    b = SamplePointsAroundmesh(p2, bmin, vs, num_per_grid=4, grid_resolution=[512, 512, 384], device="cuda:0")
+    assert a.shape == b.shape and a.shape[0] > 50000 and np.array_equal(a, b)
+    assert np.array_equal(p2[:, 1:], -pts[:, 1:])                # the reference's in-place flip of the argument
+
+
+def test_depth_rasteriser_vs_oracle_and_pmvo_convention(tmp_path):
+    """mh_render_depth against the numpy restatement of the reference's OpenGL depth pass (oracle/render_oracle.py, parity
+    unpinned: moderngl is absent), and against PMVO's own projection: a surface point projected by the PMVO kernels must see
+    itself in the rendered depth map (visibility ~1), which ties the rasteriser's pixel convention to project_points."""
+    from monohair_b200 import synthetic as syn
+    from monohair_b200.camera import cameras_from_scene
+    from monohair_b200.render import DepthRenderer
+    from oracle import render_oracle as RO
+    # an ellipsoid mesh (the synthetic capture's shape)
+    nu, nv = 48, 96
+    th, ph = np.meshgrid(np.linspace(0.05, np.pi - 0.05, nu), np.linspace(0, 2 * np.pi, nv, endpoint=False), indexing="ij")
+    r = np.array(syn.RADII)
+    V = np.stack([r[0] * np.sin(th) * np.cos(ph), r[1] * np.cos(th), r[2] * np.sin(th) * np.sin(ph)], -1).reshape(-1, 3)
+    F = []
+    for i in range(nu - 1):
+        for j in range(nv):
+            a, b, c, d = i * nv + j, i * nv + (j + 1) % nv, (i + 1) * nv + j, (i + 1) * nv + (j + 1) % nv
+            F += [[a, c, b], [b, c, d]]
+    F = np.array(F, np.int32)
+    sc = syn.make_scene(V=20, H=90, W=160, seed=4)
+    cams = cameras_from_scene(sc)
+    R = DepthRenderer(sc.H, sc.W)
+    R.add_mesh(V, F)
+    for name in list(cams)[:3]:
+        c = cams[name]
+        d = R.draw(c).cpu().numpy()
+        o = RO.render_depth(V, F, c.pose.numpy(), c.ndc_prj, sc.H, sc.W)
+        cover_same = ((d < 1) == (o < 1))
+        both = (d < 1) & (o < 1)
+        assert cover_same.mean() > 0.999 and both.sum() > 500
+        assert np.abs(d - o)[both].max() < 2e-5 or np.mean(np.abs(d - o)[both] < 2e-5) > 0.995   # silhouette-edge pixels may pick the other face
+    # PMVO sees the rendered surface as visible: depth maps from the rasteriser, analytic everything else
+    from monohair_b200.pmvo import PMVO
+    depth = np.stack([R.draw(cams[k]).cpu().numpy() for k in cams]).astype(np.float32) * 255.0
+    pm = PMVO.from_u8(cams, depth, sc.ori_gray, sc.conf_u8, sc.mask_u8, device="cuda:0", image_size=[sc.H, sc.W], patch_size=5,
+                      visible_threshold=1, conf_threshold=0.15)
+    pm.Compute_Visible_and_Ori(V[::7].astype(np.float32))
+    vis = pm.visible.cpu().numpy()
+    front = vis > 0.5
+    assert front.sum() > 0.25 * vis.size                            # a surface point is visible from the cameras facing it
+    assert np.median(vis[front]) > 0.9
