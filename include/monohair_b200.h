@@ -254,6 +254,14 @@ int mh_strand_occupancy(void* stream, const double* points, const int64_t* offse
                         const double* shift, const void* volume, int32_t gx, int32_t gy, int32_t gz, int32_t voxel_space,
                         double* frac);
 
+/* mh_accept_strands mode 0 over all SMs: what depends on geometry alone (seed-voxel hashes, dependency rows, first visits
+ * of a voxel) is computed for every batch of 512 strands at once, one CTA per batch; one CTA then walks the batches in
+ * order doing only the flag reads, the contested-strand resolution and the flag bumps.  Same result as mh_accept_strands. */
+int64_t mh_accept_strands_workspace_bytes(int64_t n, int64_t total_points);
+int mh_accept_strands_ws(void* stream, const float* points, const int64_t* offsets, const int32_t* lengths, const float* seeds,
+                         int64_t n, int64_t total_points, int32_t gx, int32_t gy, int32_t gz, float* flag, uint8_t* accepted,
+                         void* workspace, int64_t workspace_bytes);
+
 /* ---- strand smoothing (Utils/Utils.py:1148-1198 smnooth_strand / smooth_strands; HairGrow.py:914, :950, :975) ---- */
 /* Per strand (points[offsets[i] .. +lengths[i])) and axis: least squares of [lap*L ; pos*I] x = [0 ; pos*s] with L the
  * second-difference operator (first differences at the ends), solved in float64 through the pentadiagonal normal

@@ -71,6 +71,8 @@ _SIGS = {
     "mh_trace_write": (C.c_int, [p, p, i32, i32, i32, p, i64, f32, i32, p, p, p, i32, p]),
     "mh_trace_from_scalp": (C.c_int, [p, p, i32, i32, i32, p, p, i64, f32, i32, i32, p, p]),
     "mh_accept_strands": (C.c_int, [p, p, p, p, p, i64, i32, i32, i32, i32, p, p]),
+    "mh_accept_strands_workspace_bytes": (i64, [i64, i64]),
+    "mh_accept_strands_ws": (C.c_int, [p, p, p, p, p, i64, i64, i32, i32, i32, p, p, p, i64]),
     "mh_sample_mark_cells": (C.c_int, [p, p, i64, p, f64, i32, i32, i32, p]),
     "mh_sample_cells": (C.c_int, [p, p, i64, i32, p, p, f64, p]),
     "mh_render_depth": (C.c_int, [p, p, i64, p, i64, p, i32, i32, p, p, i32]),

@@ -269,6 +269,147 @@ accept_batch_kernel(const float* __restrict__ pts, const int64_t* __restrict__ o
     }
 }
 
+// ---- the ordered acceptance over all SMs ------------------------------------------------------------------------------
+// Only two things in a batch depend on the batches before it: the flag at each seed voxel when the batch starts, and which
+// strands end up kept.  Everything else -- the seed-voxel hash, the dependency rows (strand j runs through the seed voxel
+// of a later strand i) and which points of a strand are the first visit of their voxel -- depends on geometry alone, so
+// it is computed for ALL batches at once, one CTA per batch (accept_prepare_kernel), for the superset "every traced
+// strand" (a strand that turns out not to be a candidate is never kept, so its edges count for nothing).  What stays
+// sequential (accept_resolve_kernel, one CTA) is per batch: 512 flag reads, the resolution of the contested strands in
+// index order, and the flag bumps of the kept ones.
+__global__ void __launch_bounds__(A_THREADS)
+accept_prepare_kernel(const float* __restrict__ pts, const int64_t* __restrict__ offsets, const int* __restrict__ lengths,
+                      const float* __restrict__ seeds, int64_t n, int gx, int gy, int gz, unsigned* __restrict__ depg,
+                      uint8_t* __restrict__ firstocc) {
+    extern __shared__ __align__(16) unsigned char a_smem[];
+    int* hkey = reinterpret_cast<int*>(a_smem);                   // [AHT] seed voxel or -1
+    int* hhead = hkey + AHT;                                      // [AHT] first strand with that seed voxel
+    int* snext = hhead + AHT;                                     // [AB]
+    int* slen = snext + AB;                                       // [AB]
+    unsigned* dep = reinterpret_cast<unsigned*>(slen + AB);       // [AB][AB_WORDS]
+    int* vbuf = reinterpret_cast<int*>(dep + AB * AB_WORDS);      // [32][A_MAXLEN]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Vol g; g.v = nullptr; g.gx = gx; g.gy = gy; g.gz = gz;
+    const int64_t b0 = (int64_t)blockIdx.x * AB;
+    const int nb = (int)min((int64_t)AB, n - b0);
+    for (int k = tid; k < AHT; k += A_THREADS) { hkey[k] = -1; hhead[k] = -1; }
+    for (int k = tid; k < AB * AB_WORDS; k += A_THREADS) dep[k] = 0u;
+    __syncthreads();
+    if (tid < nb) {
+        const int64_t i = b0 + tid;
+        const int len = lengths[i];
+        slen[tid] = len;
+        if (len > 0) {
+            const int sv = vox_index(g, seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+            unsigned h = accept_hash(sv);
+            for (;;) {
+                const int old = atomicCAS(&hkey[h], -1, sv);
+                if (old == -1 || old == sv) { snext[tid] = atomicExch(&hhead[h], tid); break; }
+                h = (h + 1) & (AHT - 1);
+            }
+        }
+    }
+    __syncthreads();
+    int* vb = vbuf + warp * A_MAXLEN;
+    for (int j = warp; j < nb; j += A_THREADS / 32) {
+        const int len = slen[j];
+        if (len <= 0) continue;                                    // warp-uniform
+        const float* p = pts + 3 * offsets[b0 + j];
+        for (int k = lane; k < len; k += 32) {
+            const int v = vox_index(g, p[3 * k], p[3 * k + 1], p[3 * k + 2]);
+            if (k < A_MAXLEN) vb[k] = v;
+            unsigned h = accept_hash(v);
+            for (;;) {
+                const int key = hkey[h];
+                if (key == -1) break;
+                if (key == v) {
+                    for (int i = hhead[h]; i != -1; i = snext[i])
+                        if (i > j) atomicOr(&dep[i * AB_WORDS + (j >> 5)], 1u << (j & 31));
+                    break;
+                }
+                h = (h + 1) & (AHT - 1);
+            }
+        }
+        __syncwarp();
+        uint8_t* fo = firstocc + offsets[b0 + j];
+        const int l2 = min(len, A_MAXLEN);
+        for (int k = lane; k < l2; k += 32) {
+            const int v = vb[k];
+            bool first = true;
+            for (int k2 = k - 1; k2 >= 0; --k2) if (vb[k2] == v) { first = false; break; }
+            fo[k] = first ? 1 : 0;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    unsigned* dg = depg + (size_t)blockIdx.x * AB * AB_WORDS;
+    for (int k = tid; k < AB * AB_WORDS; k += A_THREADS) dg[k] = dep[k];
+}
+
+__global__ void __launch_bounds__(A_THREADS)
+accept_resolve_kernel(const float* __restrict__ pts, const int64_t* __restrict__ offsets, const int* __restrict__ lengths,
+                      const float* __restrict__ seeds, int64_t n, int gx, int gy, int gz, const unsigned* __restrict__ depg,
+                      const uint8_t* __restrict__ firstocc, float* flag, uint8_t* __restrict__ accepted) {
+    __shared__ int slen[AB];
+    __shared__ float sbase[AB];
+    __shared__ unsigned candm[AB_WORDS], keptm[AB_WORDS], contm[AB_WORDS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Vol g; g.v = nullptr; g.gx = gx; g.gy = gy; g.gz = gz;
+    int64_t bi = 0;
+    for (int64_t b0 = 0; b0 < n; b0 += AB, ++bi) {
+        const int nb = (int)min((int64_t)AB, n - b0);
+        const unsigned* dg = depg + (size_t)bi * AB * AB_WORDS;
+        if (tid < AB_WORDS) { candm[tid] = 0u; keptm[tid] = 0u; contm[tid] = 0u; }
+        __syncthreads();
+        bool cand = false;
+        if (tid < nb) {
+            const int64_t i = b0 + tid;
+            const int len = lengths[i];
+            const int sv = vox_index(g, seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+            const float base = __ldcg(flag + sv);                  // L2: earlier batches updated it with atomics
+            slen[tid] = len;
+            sbase[tid] = base;
+            cand = len > 0 && !(base >= 3.0f);
+            if (cand) atomicOr(&candm[tid >> 5], 1u << (tid & 31));
+        }
+        __syncthreads();
+        if (tid < nb && cand) {
+            unsigned any = 0u;
+#pragma unroll
+            for (int w = 0; w < AB_WORDS; ++w) any |= dg[tid * AB_WORDS + w] & candm[w];
+            atomicOr(any ? &contm[tid >> 5] : &keptm[tid >> 5], 1u << (tid & 31));
+        }
+        __syncthreads();
+        if (warp == 0) {                                            // contested candidates, in index order
+            for (int w = 0; w < AB_WORDS; ++w) {
+                unsigned word = contm[w];
+                while (word) {
+                    const int b = __ffs(word) - 1;
+                    const int i = w * 32 + b;
+                    int c = (lane < AB_WORDS) ? __popc(dg[i * AB_WORDS + lane] & keptm[lane]) : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    if (lane == 0 && sbase[i] + (float)c < 3.0f) keptm[w] |= 1u << b;
+                    __syncwarp();
+                    word &= word - 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < nb) accepted[b0 + tid] = (keptm[tid >> 5] >> (tid & 31)) & 1u;
+        for (int j = warp; j < nb; j += A_THREADS / 32) {           // kept strands bump the flag once per unique voxel
+            if (!((keptm[j >> 5] >> (j & 31)) & 1u)) continue;    // warp-uniform
+            const float* p = pts + 3 * offsets[b0 + j];
+            const uint8_t* fo = firstocc + offsets[b0 + j];
+            const int len = min(slen[j], A_MAXLEN);
+            for (int k = lane; k < len; k += 32)
+                if (fo[k]) atomicAdd(flag + vox_index(g, p[3 * k], p[3 * k + 1], p[3 * k + 2]), 1.0f);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 static int check_vol(const void* volume, int gx, int gy, int gz) {
@@ -309,6 +450,34 @@ extern "C" int mh_trace_from_scalp(void* stream, const void* volume, int32_t gx,
     MH_CHECK_ARG(roots && normals && points_out && length && max_steps > 0, "bad arguments");
     Vol g{reinterpret_cast<const float4*>(volume), gx, gy, gz};
     trace_scalp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, roots, normals, n, thr_dot, max_steps, max_inner, points_out, length);
+    MH_COUNT_LAUNCH();
+    MH_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int64_t mh_accept_strands_workspace_bytes(int64_t n, int64_t total_points) {
+    const int64_t nbatch = (n + AB - 1) / AB;
+    return nbatch * AB * AB_WORDS * 4 + ((total_points + 15) / 16) * 16 + 256;
+}
+
+/* mode 0 with a workspace: the geometry-only part of every batch on all SMs, then the short sequential resolution */
+extern "C" int mh_accept_strands_ws(void* stream, const float* points, const int64_t* offsets, const int32_t* lengths,
+                                    const float* seeds, int64_t n, int64_t total_points, int32_t gx, int32_t gy, int32_t gz,
+                                    float* flag, uint8_t* accepted, void* workspace, int64_t workspace_bytes) {
+    if (n == 0) return 0;
+    MH_CHECK_ARG(points && offsets && lengths && flag && accepted && seeds && workspace, "null pointer");
+    MH_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && total_points >= 0, "bad arguments");
+    MH_CHECK_ARG(workspace_bytes >= mh_accept_strands_workspace_bytes(n, total_points), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nbatch = (n + AB - 1) / AB;
+    unsigned* depg = reinterpret_cast<unsigned*>(workspace);
+    uint8_t* firstocc = reinterpret_cast<uint8_t*>(depg + nbatch * AB * AB_WORDS);
+    const size_t smem = sizeof(int) * (2 * AHT + 2 * AB) + sizeof(unsigned) * (AB * AB_WORDS) + sizeof(int) * 32 * A_MAXLEN;
+    cudaError_t e = cudaFuncSetAttribute(accept_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mh_set_error("mh_accept_strands_ws: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 2; }
+    accept_prepare_kernel<<<(unsigned)nbatch, A_THREADS, smem, st>>>(points, offsets, lengths, seeds, n, gx, gy, gz, depg, firstocc);
+    MH_COUNT_LAUNCH();
+    accept_resolve_kernel<<<1, A_THREADS, 0, st>>>(points, offsets, lengths, seeds, n, gx, gy, gz, depg, firstocc, flag, accepted);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;

@@ -88,6 +88,14 @@ class HairGrowing:
     def _accept(self, pts, offsets, lengths, seeds, flag, mode):
         n = lengths.numel()
         acc = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        if mode == 0 and seeds is not None and n > 0:
+            total = int(pts.size(0))
+            wsb = lib().mh_accept_strands_workspace_bytes(n, total)
+            ws = torch.empty((wsb,), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                check(lib().mh_accept_strands_ws(stream_ptr(self.device), ptr(pts), ptr(offsets), ptr(lengths), ptr(seeds), n, total,
+                                                 self.gx, self.gy, self.gz, ptr(flag), ptr(acc), ptr(ws), wsb), "mh_accept_strands_ws")
+            return acc.bool()
         with torch.cuda.device(self.device):
             check(lib().mh_accept_strands(stream_ptr(self.device), ptr(pts), ptr(offsets), ptr(lengths),
                                           ptr(seeds) if seeds is not None else None, n, self.gx, self.gy, self.gz, mode,
