@@ -31,6 +31,11 @@ WORKLOADS = {
     # conf_threshold .15, threshold .025, num_sample_per_grid 4), 60 views, grid 256x256x192
     "full": dict(name="pmvo_big_wavy1_synth_60v_1920x1080", V=60, H=1920, W=1080, patch=7, conf_thr=0.15, thr=0.025,
                  visible_thr=1, num_per_grid=4, n_cells=None),
+    # BASELINE.json configs[4]: PMVO + HairGrow, 120 views @ 2160p, 512 x 512 x 384 grid (0.625 mm candidate cells, 1.25 mm
+    # voxels), meant for 8 GPUs (32 GB of view maps per rank); run by hand: --scale cfg5 --no-e2e --no-cpu --no-extra
+    "cfg5": dict(name="pmvo_hairgrow_120v_2160x3840_grid512x512x384", V=120, H=2160, W=3840, patch=7, conf_thr=0.15, thr=0.025,
+                 visible_thr=1, num_per_grid=4, n_cells=None, fine_vsize=0.005 / 8, fine_grid=(1024, 1024, 768),
+                 grid=(512, 512, 384), voxel_size=0.005 / 4, hairgrow=True),
     "small": dict(name="pmvo_small_24v_480x270", V=24, H=480, W=270, patch=7, conf_thr=0.15, thr=0.025,
                   visible_thr=1, num_per_grid=2, n_cells=20000),
 }
@@ -88,11 +93,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_workload(cfg, device, seed=0):
+def make_workload(cfg, device, seed=0, views=None):
     from monohair_b200 import synthetic as syn
     t = time.time()
-    sc = syn.make_scene(V=cfg["V"], H=cfg["H"], W=cfg["W"], seed=seed, device=device)
-    cand = syn.candidate_points(n_cells=cfg["n_cells"], num_per_grid=cfg["num_per_grid"], seed=seed)
+    sc = syn.make_scene(V=cfg["V"], H=cfg["H"], W=cfg["W"], seed=seed, device=device, views=views)
+    kw = {}
+    if "fine_vsize" in cfg:
+        kw = dict(vsize=cfg["fine_vsize"], grid=cfg["fine_grid"])
+    cand = syn.candidate_points(n_cells=cfg["n_cells"], num_per_grid=cfg["num_per_grid"], seed=seed, **kw)
     scalp = syn.scalp_vertices(2000, seed=seed)
     log(f"workload {cfg['name']}: scene+candidates in {time.time() - t:.1f}s, {cand.shape[0]} candidate points")
     return sc, cand, scalp
@@ -125,7 +133,7 @@ def cpu_port_step(vm, cand_sample, cfg, scalp):
 def config_dict(cfg):
     """the workload, in the same words for both arms (the driver compares the two `config` objects)."""
     return {"workload": cfg["name"], "views": cfg["V"], "image": [cfg["H"], cfg["W"]], "patch": cfg["patch"],
-            "grid": [256, 256, 192], "num_sample_per_grid": cfg["num_per_grid"],
+            "grid": list(cfg.get("grid", (256, 256, 192))), "num_sample_per_grid": cfg["num_per_grid"],
             "cache": "inputs larger than L2 (%.1f GB of view maps, gathered)" % ((cfg["V"] * cfg["H"] * cfg["W"] * 32) / 1e9)}
 
 
@@ -181,7 +189,13 @@ def run_b200(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    sc, cand_np, scalp = make_workload(cfg, dev)
+    views = None
+    if world > 1 and cfg.get("hairgrow"):                      # big captures: a rank generates only the views it uploads
+        per = (cfg["V"] + world - 1) // world
+        views = range(min(rank * per, cfg["V"]), min((rank + 1) * per, cfg["V"]))
+    sc, cand_np, scalp = make_workload(cfg, dev, views=views)
+    grid = tuple(cfg.get("grid", (256, 256, 192)))
+    voxel_size = float(cfg.get("voxel_size", 0.005 / 2))
     P.scalp_tree, P.scalp_max = scalp, scalp.max(0)
     cams = cameras_from_scene(sc)
     kw = dict(device=dev, image_size=[cfg["H"], cfg["W"]], patch_size=cfg["patch"], visible_threshold=cfg["visible_thr"],
@@ -208,7 +222,7 @@ def run_b200(args, cfg):
             e = torch.cuda.Event(enable_timing=True)
             e.record(torch.cuda.current_stream(dev))
             evs.append((name, e))
-        out = pipeline.pmvo_job_device(pm, cand, cfg["thr"], stats=stats, mark=mark)
+        out = pipeline.pmvo_job_device(pm, cand, cfg["thr"], stats=stats, mark=mark, grid=grid, voxel_size=voxel_size)
         if record:
             all_events.append(evs)          # elapsed times are read after the timed region (no extra sync inside it)
         return out
@@ -272,7 +286,7 @@ def run_b200(args, cfg):
     # + 12 B point + 20 B counters per point.  (The reference's own formulation gathers 204 B per pair)
     filt_bytes = ((n_cov + world - 1) // world) * (cfg["V"] * 12 + 12 + 20)
     n_fused = stats["n_selected"] + stats["n_fu"]
-    nvox = 256 * 256 * 192
+    nvox = grid[0] * grid[1] * grid[2]
     fuse_bytes = n_fused * 28 + n_fused * 2 * 8 + nvox * 16                      # SURVEY §8d voxel fusion
     # optimize_kernel (83 % of the step) is instruction-issue bound, not HBM bound (profiles/r2_optimize_ncu.md):
     # its ruler is the SM's measured issue rate (tools/microbench_peaks.cu -> profiles/r2_fp32_peaks.json), against the
@@ -309,6 +323,33 @@ def run_b200(args, cfg):
                        "frac": fuse_bytes / (med["fuse"] * 1e-3) / 1e9 / hbm_peak, "ms": med["fuse"], "peak_source": peak_src},
         "filter_count": {"achieved": filt_bytes / (med["filter"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": filt_bytes / (med["filter"] * 1e-3) / 1e9 / hbm_peak, "ms": med["filter"], "peak_source": peak_src}}
+
+    # ---- BASELINE configs[4]: the strand stage on the fused volume, straight from device memory (rank 0) ------------
+    hairgrow = None
+    if cfg.get("hairgrow") and rank == 0:
+        import contextlib
+        from monohair_b200 import synthetic as syn
+        from monohair_b200.hairgrow import HairGrowing
+        with contextlib.redirect_stdout(sys.stderr):
+            hg = HairGrowing(volume=out["volume"], device=dev)
+            rng = np.random.default_rng(0)
+            d = rng.normal(size=(400000, 3)); d /= np.linalg.norm(d, axis=-1, keepdims=True); d = d[d[:, 1] > 0.2][:60000]
+            r = np.array(syn.RADII) * 0.9
+            pp = d * r
+            nrm = pp / (r * r); nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+            flip = np.array([1.0, -1.0, -1.0])
+            roots = torch.from_numpy(((pp * flip - syn.BBOX_MIN) / voxel_size).astype(np.float32)).to(dev)
+            normals = torch.from_numpy((nrm * flip).astype(np.float32)).to(dev)
+            torch.manual_seed(0)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            strands, num_root = hg.GenerateGuideStrandFromScalp(roots, normals, None, 0.85)
+            torch.cuda.synchronize()
+            hairgrow = {"s": time.time() - t0, "strands": len(strands), "num_root": int(num_root),
+                        "points": int(sum(x.shape[0] for x in strands)), "occupied_voxels": int(out["volume"][..., 3].sum().item())}
+            del strands, hg
+    if world > 1 and cfg.get("hairgrow"):
+        dist.barrier()
 
     # ---- end to end from host buffers ----------------------------------------------------------------------
     e2e = None
@@ -415,7 +456,7 @@ def run_b200(args, cfg):
                         f"fusion {os.environ.get('MH_FUSE_DIST', 'replicated')}"},
                 "checksums": checksums,
                 "stage_ms": med, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "other_workloads": other}
+                "clocks": clocks, "other_workloads": other, "hairgrow_on_fused_volume": hairgrow}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -430,11 +471,15 @@ def main():
     ap.add_argument("--scale", default=os.environ.get("MH_BENCH_SCALE", "full"), choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--override", default=None, help='JSON dict merged into the workload (smoke tests of big configs, e.g. {"V": 24, "H": 540, "W": 960})')
     ap.add_argument("--no-extra", action="store_true", help="skip the Gabor / HairGrow / 256^3 workloads reported beside the PMVO job")
     args = ap.parse_args()
     if args.impl == "b200":
         args.warmup = max(args.warmup, int(os.environ.get("MH_BENCH_MIN_WARMUP", "3")))   # profiling runs may lower it
-    cfg = WORKLOADS[args.scale]
+    cfg = dict(WORKLOADS[args.scale])
+    if args.override:
+        cfg.update(json.loads(args.override))
+        cfg["name"] += "_override"
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

@@ -180,7 +180,7 @@ def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.V
     return P.voxel_scatter(allw, dev, grid)
 
 
-def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
+def pmvo_job_device(pm, cand, threshold, stats=None, mark=None, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE):
     """Whole PMVO job with everything resident on the device.  cand float32 [N,3].  -> dict.
     `mark(name)` (optional) is called at stage boundaries (bench.py records CUDA events there)."""
     mark = mark or (lambda name: None)
@@ -209,7 +209,7 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None):
         fh = center = None
         all_p, all_o, valid = sp, so, None
     mark("unvisible")
-    vol = fuse_stage(pm, all_p, all_o, valid=valid)
+    vol = fuse_stage(pm, all_p, all_o, grid=grid, voxel_min=voxel_min, voxel_size=voxel_size, valid=valid)
     mark("fuse")
     if center is not None:
         fo, fp = center[~fh], fu[~fh]

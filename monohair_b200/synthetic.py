@@ -115,7 +115,10 @@ def flow_tangent(X, radii):
 
 
 def make_scene(V=24, H=270, W=480, seed=0, device="cpu", ori_noise_deg=4.0, radii=RADII,
-               radius=0.8, focal_px=None) -> Scene:
+               radius=0.8, focal_px=None, views=None) -> Scene:
+    """`views` (optional range): fill only those views' maps (a rank of a view-sharded upload needs only its block; the
+    random stream is consumed for every view, so a view looks the same whoever generates it); the other views' maps are
+    left uninitialised."""
     dev = torch.device(device)
     g = torch.Generator().manual_seed(seed)
     cams = make_cameras(V, H, W, radius=radius, focal_px=focal_px)
@@ -127,6 +130,10 @@ def make_scene(V=24, H=270, W=480, seed=0, device="cpu", ori_noise_deg=4.0, radi
     rows = torch.arange(H, dtype=torch.float64, device=dev)[:, None].expand(H, W)
     cols = torch.arange(W, dtype=torch.float64, device=dev)[None, :].expand(H, W)
     for i, c in enumerate(cams):
+        if views is not None and i not in views:
+            torch.randn((H, W), generator=g, dtype=torch.float64)
+            torch.rand((H, W), generator=g, dtype=torch.float64)
+            continue
         fx, fy, cx, cy = c["ndc_prj"]
         pose = torch.tensor(c["pose"], dtype=torch.float64, device=dev)      # c2w
         R, eye = pose[:3, :3], pose[:3, 3]
