@@ -108,3 +108,30 @@ def test_scalp_normals_interpolate_vertex_normals(tmp_path):
     q.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
     v, f, vn = read_obj_normals(str(q))
     assert np.allclose(vn, [[0, 0, 1]] * 4)
+
+
+def test_connect_strands_and_chain_following_host_logic():
+    """HairGrow.py:303-421 host side: connect_strands extends a piece list by the SHAPE of the partner (its successive
+    differences) from the free end, through the mid point with the partner's facing end; connect_segments follows the
+    connection table through each partner's other end and stops at a strand already on the chain."""
+    import numpy as np
+    from monohair_b200.hairgrow_connect import connect_segments, connect_strands
+    a = np.array([[0., 0, 0], [1, 0, 0], [2, 0, 0]])
+    b = np.array([[2.2, 0, 0], [3.2, 1, 0], [4.2, 1, 0]])
+    out = connect_strands([a.copy()], b, push_back=True)
+    assert len(out) == 2 and out[1].shape == (3, 3)
+    mid = a[-1] * 0.5 + b[0] * 0.5
+    assert np.allclose(out[1][0], mid) and np.allclose(np.diff(out[1], axis=0), np.diff(b, axis=0))
+    out = connect_strands([a.copy()], b[::-1], push_back=False)          # prepend: partner's tip faces our root
+    assert len(out) == 2 and np.allclose(out[0][-1], a[0] * 0.5 + b[::-1][-1] * 0.5)
+    # three strands in a row: 0.tip -> 1.root, 1.tip -> 2.root; info = {root partner, its end, tip partner, its end}
+    s0, s1, s2 = a, a + [2.1, 0, 0], a + [4.2, 0, 0]
+    info = np.array([[-1, 0, 1, 1], [0, 2, 2, 1], [1, 2, -1, 0]], np.int32)
+    long0 = connect_segments(info, [s0, s1, s2], 0)
+    assert long0.shape[0] == 9 and np.all(np.diff(long0[:, 0]) > 0)      # grown through both partners, monotone along x
+    long1 = connect_segments(info, [s0, s1, s2], 1)
+    assert long1.shape[0] == 9 and np.all(np.diff(long1[:, 0]) > 0)
+    # a cycle: the chain check only guards the recursive step (HairGrow.py:331-333), so both of strand 0's own ends still
+    # take their partner, but neither side continues back into strand 0
+    cyc = np.array([[1, 2, 1, 1], [0, 2, 0, 1]], np.int32)
+    assert connect_segments(cyc, [s0, s1], 0).shape[0] == 9
