@@ -12,9 +12,14 @@ import torch
 from . import pmvo_oracle as O
 
 
-def forward_margins(vm, points, P, conf_threshold):
+def forward_margins(vm, points, P, conf_threshold, eps=5e-8, with_threshold_gap=False):
     """PMVO.forward (PMVO.py:39-78): gap between the winning (base view, depth sample) loss and the runner-up over all
-    (valid base, sample) pairs.  -> margin float64 [N] (inf when there is a single candidate)."""
+    (valid base, sample) pairs.  -> margin float64 [N] (inf when there is a single candidate).
+
+    with_threshold_gap: also return, per point, how close a confidence test that feeds the choice was to flipping
+    (PMVO.py:196-205): min |sum(w)/count - conf_threshold| over the (valid base, sample) pairs whose flip would matter --
+    the winner itself (its loss turns into 1 / its high-confidence flag changes), a masked pair whose raw loss would
+    win (raw < winning loss + eps), and every pair of a base whose positive count sits at the `< 5` boundary (4 or 5)."""
     _, _, _, _, dbg = O.forward(vm, points, P, conf_threshold, debug=True)
     L = torch.stack(dbg["L"], 0).double()                       # [10, N, S]
     valid = (dbg["base_conf"] > 0)                              # [10, N]; base 0 is taken unconditionally (PMVO.py:57-64)
@@ -25,7 +30,38 @@ def forward_margins(vm, points, P, conf_threshold):
     two = torch.topk(flat, 2, dim=1, largest=False).values
     m = two[:, 1] - two[:, 0]
     m = torch.where(torch.isnan(m), torch.zeros_like(m), m)
-    return m.numpy()
+    if not with_threshold_gap:
+        return m.numpy()
+    raw = torch.stack([d["raw"] for d in dbg["detail"]], 0).double()
+    ratio = torch.stack([d["ratio"] for d in dbg["detail"]], 0).double()
+    pos = torch.stack([d["pos"] for d in dbg["detail"]], 0)
+    npos = pos.sum(-1)                                          # [10, N]
+    win = two[:, 0][None, :, None]
+    matters = (L <= win) | (~pos & (raw < win + eps)) | ((npos == 4) | (npos == 5))[:, :, None]
+    matters &= valid[:, :, None]
+    gap = torch.where(matters, (ratio - conf_threshold).abs(), torch.full_like(ratio, float("inf")))
+    gap = torch.where(torch.isnan(gap), torch.zeros_like(gap), gap)
+    return m.numpy(), gap.amin(dim=(0, 2)).numpy()
+
+
+def singleton_base_groups(vm, points, P, chunk):
+    """Points whose depth samples the reference computes on a batch of ONE (PMVO.py:290-296: sample_next_3d_pos projects
+    `points[base_view == v]` per view).  When a point is the only one of its forward() chunk with view v at some used
+    base rank, torch.matmul(pose, hom[4,1]) takes MKL's matrix-vector path, whose accumulation order differs from the
+    sgemm path every other point sees (44 % of such projections move by an ulp) -- the reference's result for such a
+    point depends on what else happens to be in its chunk, so it is reported separately, not as a kernel difference.
+    -> bool [N]"""
+    pts = torch.from_numpy(np.asarray(points)).type(torch.float)
+    out = np.zeros(pts.size(0), dtype=bool)
+    for lo in range(0, pts.size(0), chunk):
+        sub = pts[lo:lo + chunk]
+        st = O.compute_visible_and_ori(vm, sub, P)
+        bidx, bval, _ = O.find_base_views(st["visible"], st["Conf"])
+        for r, i in enumerate(range(0, 20, 2)):
+            used = (bval[i] > 0) if r else torch.ones_like(bval[i], dtype=torch.bool)   # rank 0 is taken unconditionally
+            cnt = torch.bincount(bidx[i], minlength=vm.V)
+            out[lo:lo + chunk] |= ((cnt[bidx[i]] == 1) & used).numpy()
+    return out
 
 
 def _medoid_gap(ori_nk3):

@@ -288,7 +288,8 @@ def compute_prj_loss(state, prj, conf_threshold, return_all=False):
     w = torch.where(vis == -1, torch.zeros_like(vis), torch.ones_like(vis))[:, :, None] * best_c   # compute_weight (:211-215)
     lw = loss * w
     sw = torch.sum(w, dim=0)
-    pos = (sw / torch.sum(w > 0, dim=0)) > conf_threshold     # [N,S]
+    ratio = sw / torch.sum(w > 0, dim=0)
+    pos = ratio > conf_threshold                              # [N,S]
     low = torch.sum(pos, dim=-1) < 5                          # [N]
     L = torch.sum(lw, dim=0) / sw
     raw = L.clone()
@@ -296,6 +297,8 @@ def compute_prj_loss(state, prj, conf_threshold, return_all=False):
     L[low] = raw[low]
     mn, am = torch.min(L, dim=-1)
     hc = pos[torch.arange(pos.size(0)), am]
+    if return_all == "detail":                                # for oracle/margins.py: the decisions behind L
+        return mn, am, hc, L, dict(raw=raw, ratio=ratio, pos=pos, low=low)
     if return_all:
         return mn, am, hc, L
     return mn, am, hc
@@ -314,8 +317,9 @@ def forward(vm: ViewMaps, points_np, P, conf_threshold, debug=False):
         smp = sample_next_3d_pos(vm, pts, bidx[i], st["Ori"])
         prj = compute_reproject_ori(vm, pts, smp)
         if debug:
-            loss, am, hc, L = compute_prj_loss(st, prj, conf_threshold, return_all=True)
+            loss, am, hc, L, det = compute_prj_loss(st, prj, conf_threshold, return_all="detail")
             dbg["L"].append(L)
+            dbg.setdefault("detail", []).append(det)
             dbg["arg"].append(am.clone())
             dbg["loss_b"].append(loss.clone())
         else:

@@ -4,10 +4,17 @@ closer to flipping than the eps below; excluded items are counted and printed, a
 
 The kernels follow the reference's fp32 operation order, so the eps are a few ulps of the compared quantity, not
 "percent of items allowed to differ":
-  EPS_FWD   5e-8  winning vs runner-up (base view, depth sample) loss; a loss is sum(l*w)/sum(w) with sums of a few units,
+  EPS_FWD   2e-8  winning vs runner-up (base view, depth sample) loss; a loss is sum(l*w)/sum(w) with sums of a few units,
                   and the one known order deviation (torch.sum's interleaved tail columns) moves either sum by
-                  an ulp: <= ~1e-8 on a loss (largest deviation seen at BASELINE scale: 9.4e-9), so two candidate losses
-                  closer than 5e-8 may legitimately swap (2.6 % of the items at BASELINE scale)
+                  an ulp: <= ~1e-8 on a loss, so two candidate losses closer than 2e-8 may legitimately swap (1.2 % of the
+                  items at BASELINE scale)
+  EPS_THR   1e-7  | sum(w)/count - conf_threshold | of the confidence tests that feed that choice (same sums, same deviation)
+  singleton       points the reference sampled in a batch of one: torch.matmul takes MKL's matrix-vector path there, whose
+                  accumulation order differs from the sgemm path every other point sees, i.e. the reference's own result
+                  for such a point depends on what else is in its forward() chunk (oracle/margins.py:singleton_base_groups;
+                  0.5 % of the items at BASELINE scale).  The kernel reproduces the sgemm order; these points are listed
+                  and compared at 5e-4 on the direction (an ulp or two of a coordinate over a sub-millimetre step) instead of bit
+                  for bit.
   EPS_KNN   1e-13 gap between consecutive neighbour distances (float64, ~1e-3 m): set membership and summation order
   EPS_UPD   2e-7  | |cos(center, ori)| - 0.95 |, the update threshold of refine step (i)
   EPS_SEL   2e-8  | refine loss - threshold |, membership of the selected set
@@ -17,23 +24,35 @@ certain; the number of medoids whose top-2 gap is below 1e-6 is printed to show 
 """
 import numpy as np
 
-EPS_FWD, EPS_KNN, EPS_UPD, EPS_SEL, EPS_ROUND = 5e-8, 1e-13, 2e-7, 2e-8, 1e-9
+EPS_FWD, EPS_THR, EPS_KNN, EPS_UPD, EPS_SEL, EPS_ROUND = 2e-8, 1e-7, 1e-13, 2e-7, 2e-8, 1e-9
 MAX_EXCLUDED = 0.05
 
 
 def forward_gate(g):
+    """-> (keep, singleton): strict set, and the batch-of-one points taken out of it"""
     keep = g["fwd_margin"] > EPS_FWD
-    return keep
+    if "fwd_thr_gap" in g:
+        keep &= g["fwd_thr_gap"] > EPS_THR
+    single = np.asarray(g["fwd_singleton"]) if "fwd_singleton" in g else np.zeros(len(keep), dtype=bool)
+    return keep & ~single, single
 
 
 def check_forward(g, ori, loss, hc, what="forward"):
-    keep = forward_gate(g)
+    keep, single = forward_gate(g)
     n, ex = len(keep), int((~keep).sum())
     exact = np.all(ori == g["fwd_ori"], axis=1)
     dl = np.abs(loss.astype(np.float64) - g["fwd_loss"])
-    print(f"\n{what}: {n} points, {ex} excluded (oracle margin <= {EPS_FWD:g}); strict set: {exact[keep].mean() * 100:.3f}% "
+    print(f"\n{what}: {n} points, {ex} excluded (oracle margin <= {EPS_FWD:g} / threshold gap <= {EPS_THR:g}: {ex - int(single.sum())}, "
+          f"batch-of-one in the reference: {int(single.sum())}); strict set: {exact[keep].mean() * 100:.3f}% "
           f"directions bit-identical, max|dloss| {dl[keep].max():.3g}; excluded set: {exact[~keep].mean() * 100 if ex else 100:.1f}% identical")
+    sure = single & (g["fwd_margin"] > 1e-6)                       # batch-of-one points with a clear decision: same choice, ulp-level samples
+    if sure.any():
+        dev = np.abs(ori[sure] - g["fwd_ori"][sure]).max()
+        print(f"  batch-of-one points with margin > 1e-6: {int(sure.sum())}, {int(exact[sure].sum())} bit-identical, max|d ori| {dev:.3g}")
+        assert dev <= 5e-4                                      # 1-2 ulp of a ~1 m coordinate over a >= 0.5 mm step
     assert ex <= MAX_EXCLUDED * n, f"{ex} of {n} items excluded by the margin gate"
+    for i in np.flatnonzero(~exact & keep)[:8]:
+        print(f"  differs: point {i}  margin {g['fwd_margin'][i]:.3g}  loss ref {g['fwd_loss'][i]!r} gpu {loss[i]!r}  ori ref {g['fwd_ori'][i]} gpu {ori[i]}")
     assert exact[keep].all(), f"{int((~exact[keep]).sum())} directions differ on items with margin > {EPS_FWD:g}"
     assert dl[keep].max() <= 2e-8
     assert np.array_equal(hc[keep], g["fwd_hc"][keep])

@@ -4,6 +4,8 @@ For every golden written by make_golden.py / make_golden_inner.py this runs the 
 oracle itself is pinned bit-for-bit to the reference's outputs by tests/test_oracle_golden.py) on the golden's own
 inputs and stores, per item, how far the reference's discrete choice was from flipping:
   fwd_margin [n]            PMVO.forward: winning (base view, depth sample) loss vs the runner-up
+  fwd_thr_gap [n]           distance of the confidence tests behind that choice from their threshold (PMVO.py:196-205)
+  fwd_singleton [n]         the reference sampled this point in a batch of one (MKL matrix-vector path; oracle/margins.py)
   ref_knn_gap / ref_medoid_gap / ref_update_gap [n], ref_nbr [n,100]   refine step (i)
   fu_knn_gap / fu_medoid_gap [m]                                        near-surface orientations, step (iii)
   vox_round_gap [p], vox_keys / vox_medoid_gap [q]                      voxelisation
@@ -25,10 +27,14 @@ from oracle import margins as M  # noqa: E402
 from oracle import pmvo_oracle as O  # noqa: E402
 
 
-def pmvo_margins(g, vm):
-    """g: dict-like with the arrays of a PMVO golden -> dict of margin arrays."""
+def pmvo_margins(g, vm, fwd_chunk=None):
+    """g: dict-like with the arrays of a PMVO golden -> dict of margin arrays.  fwd_chunk: how many points each
+    forward() call of the reference saw when the golden was made (default: all at once)."""
     P, ct, thr = int(g["patch"]), float(g["conf_thr"]), float(g["thr"])
-    out = {"fwd_margin": M.forward_margins(vm, g["fwd_points"], P, ct)}
+    fm, tg = M.forward_margins(vm, g["fwd_points"], P, ct, with_threshold_gap=True)
+    ch = int(fwd_chunk or len(g["fwd_points"]))
+    out = {"fwd_margin": fm, "fwd_thr_gap": tg, "fwd_chunk": np.int64(ch),
+           "fwd_singleton": M.singleton_base_groups(vm, g["fwd_points"], P, ch)}
     pts32 = g["fwd_points"].astype(np.float32)
     r = M.refine_margins(pts32, g["fwd_ori"], g["ref_select_o"])
     out.update(ref_knn_gap=r["knn_gap"], ref_medoid_gap=r["medoid_gap"], ref_update_gap=r["update_gap"],
