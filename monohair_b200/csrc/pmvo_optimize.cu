@@ -144,42 +144,18 @@ MH_D void process_base(const Smem& sm, const mh_views& vw, int b, int S, int PP,
         const int ne = sm.ecnt[v];
         float bl[SPL];
         int bk[SPL];
-        // Fast form: track the first maximiser of |cos| instead of the first minimiser of l = fl(1 - |cos|).  The
-        // subtraction is exact for |cos| >= 0.5 and l >= 0.5 > 1 - max for every entry below that, so with
-        // max|cos| > 0.5 both scans pick the same entry and 1 - max is the reference's loss; otherwise (or on NaN)
-        // the reference's own scan is replayed for the whole warp.
         {
             const float2 x = exy[0];
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) { bl[j] = fabsf(x.x * y0[j] + x.y * y1[j]); bk[j] = 0; }
+            for (int j = 0; j < SPL; ++j) { bl[j] = 1.0f - fabsf(x.x * y0[j] + x.y * y1[j]); bk[j] = 0; }
         }
 #pragma unroll 4
         for (int k = 1; k < ne; ++k) {
             const float2 x = exy[k];
 #pragma unroll
             for (int j = 0; j < SPL; ++j) {
-                const float d = fabsf(x.x * y0[j] + x.y * y1[j]);
-                if (d > bl[j]) { bl[j] = d; bk[j] = k; }
-            }
-        }
-        bool sure = true;
-#pragma unroll
-        for (int j = 0; j < SPL; ++j) sure = sure && (bl[j] > 0.5f);
-        if (__all_sync(0xffffffffu, sure)) {
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) bl[j] = 1.0f - bl[j];
-        } else {
-            const float2 x0 = exy[0];
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) { bl[j] = 1.0f - fabsf(x0.x * y0[j] + x0.y * y1[j]); bk[j] = 0; }
-#pragma unroll 2
-            for (int k = 1; k < ne; ++k) {
-                const float2 x = exy[k];
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) {
-                    const float l = 1.0f - fabsf(x.x * y0[j] + x.y * y1[j]);
-                    if (l < bl[j]) { bl[j] = l; bk[j] = k; }
-                }
+                const float l = 1.0f - fabsf(x.x * y0[j] + x.y * y1[j]);
+                if (l < bl[j]) { bl[j] = l; bk[j] = k; }
             }
         }
         const float* __restrict__ ec = sm.ec + (size_t)v * PP;

@@ -688,27 +688,45 @@ extern "C" int mh_refine_update(void* stream, const float* center, const float* 
 //
 // Dependency analysis: the re-score of chunk c reads only (points, centre_c) and feeds nothing back into later
 // chunks; only the orientation update does.  So the sequential part is the medoid + update chain alone:
-//   1. refine_sweep_kernel: ONE persistent launch.  CTAs draw point tickets in index order; a CTA whose point lies
-//      in chunk c waits until chunk c-1 has retired (per-chunk completion counters, acquire/release through L2), then
-//      gathers neighbour j from `ori_new` if j's chunk is earlier than c and from the untouched input otherwise --
-//      exactly the values the reference's in-place array holds when it processes chunk c.  Tickets are drawn in order
-//      and a CTA only ever waits on earlier tickets, which are held by running CTAs: no deadlock for any grid size.
-//      Four warps share one point so that the hand-over between chunks costs a quarter of a warp-per-point medoid.
+//   1. refine_sweep_kernel: ONE persistent launch.  CTAs draw point tickets in index order.  A point of chunk c gathers
+//      neighbour j from `ori_new` if j's chunk is earlier than c and from the untouched input otherwise -- exactly the
+//      values the reference's in-place array holds when it processes chunk c.  `ori_new` starts filled with a PENDING
+//      bit pattern; a gather that meets it spins on that word until the owner has stored the final value (every word
+//      goes pending -> final exactly once, so three non-pending words ARE the final triple: no flag, no fence, no extra
+//      round trip).  The dependency is per point, not per chunk: nothing drains at a chunk boundary, only the rare
+//      neighbour that is still in flight is waited for.  Tickets are drawn in order and a CTA only ever waits on earlier
+//      tickets, which are finished or held by running CTAs: no deadlock for any grid size.
+//      Four warps share one point so that a wait costs a quarter of a warp-per-point medoid.
 //   2. one mh_pmvo_refine_loss launch over all n points with the stored centres;
 //   3. refine_finish_kernel: loss rules (head filter / -1 -> 0.5, PMVO.py:92, :639).
 namespace {
 constexpr int SW_THREADS = 128;                       // one CTA per point: the chunk hand-over costs one point's latency
 
-MH_D int sw_ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// PENDING: an all-ones NaN.  Arithmetic produces the canonical 0x7fffffff, never this pattern; a stored value that
+// carries it anyway (it can only arrive as an input NaN payload) is written as 0xfffffffe, still a NaN.
+constexpr unsigned SW_PENDING = 0xffffffffu;
+
+MH_D unsigned sw_ld(const float* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-MH_D void sw_red_release(int* p, int v) {
-    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+MH_D void sw_st(float* p, float x) {
+    unsigned v = __float_as_uint(x);
+    if (v == SW_PENDING) v = 0xfffffffeu;
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// final value of ori_new[3*rr .. 3*rr+2] (waits while its owner is still in flight)
+MH_D void sw_wait3(const float* p, float& a, float& b, float& c) {
+    unsigned ua = sw_ld(p), ub = sw_ld(p + 1), uc = sw_ld(p + 2);
+    while (ua == SW_PENDING || ub == SW_PENDING || uc == SW_PENDING) {
+        __nanosleep(64);
+        ua = sw_ld(p); ub = sw_ld(p + 1); uc = sw_ld(p + 2);
+    }
+    a = __uint_as_float(ua); b = __uint_as_float(ub); c = __uint_as_float(uc);
 }
 
-// ctl: [0] next ticket, [16 + c] retired points of chunk c
+// ctl: [0] next ticket
 __global__ void __launch_bounds__(SW_THREADS)
 refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int* __restrict__ nbr, int64_t n, int K,
                     int sub_num, float* __restrict__ center, int* ctl) {
@@ -717,25 +735,22 @@ refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int
     __shared__ float s_best[SW_THREADS / 32];
     __shared__ int s_bk[SW_THREADS / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int* done = ctl + 16;
     for (;;) {
         if (tid == 0) s_ticket = atomicAdd(ctl, 1);
         __syncthreads();
         const int t = s_ticket;
         if (t >= n) break;
         const int64_t i = t;
-        const int c = t / sub_num;
-        const int first = c * sub_num;                   // neighbours below `first` belong to earlier chunks
-        // neighbour id first (independent of the wait), then wait for the previous chunk to retire
-        const int r0 = (tid < K) ? nbr[i * K + tid] : 0;
-        if (c > 0 && tid == 0) {
-            while (sw_ld_acquire(done + c - 1) < sub_num) __nanosleep(100);
-        }
-        __syncthreads();
+        const int first = (t / sub_num) * sub_num;       // neighbours below `first` belong to earlier chunks
         for (int k = tid; k < K; k += SW_THREADS) {
-            const int rr = (k == tid) ? r0 : nbr[i * K + k];
-            const float* src = (rr < first) ? ori_new : ori_old;
-            const float a = __ldcg(src + 3 * (int64_t)rr), b = __ldcg(src + 3 * (int64_t)rr + 1), cc = __ldcg(src + 3 * (int64_t)rr + 2);
+            const int rr = nbr[i * K + k];
+            float a, b, cc;
+            if (rr < first) {
+                sw_wait3(ori_new + 3 * (int64_t)rr, a, b, cc);
+            } else {
+                const float* src = ori_old + 3 * (int64_t)rr;
+                a = __ldcg(src); b = __ldcg(src + 1); cc = __ldcg(src + 2);
+            }
             const float nn = fmaxf(mh_norm3(a, b, cc), 1e-8f);
             sw_u[k] = make_float4(a / nn, b / nn, cc / nn, 0.0f);
         }
@@ -762,15 +777,19 @@ refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int
                 if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
             }
             const int rr = nbr[i * K + bk];
-            const float* src = (rr < first) ? ori_new : ori_old;
-            const float c0 = __ldcg(src + 3 * (int64_t)rr), c1 = __ldcg(src + 3 * (int64_t)rr + 1), c2 = __ldcg(src + 3 * (int64_t)rr + 2);
+            float c0, c1, c2;
+            if (rr < first) {
+                sw_wait3(ori_new + 3 * (int64_t)rr, c0, c1, c2);           // already final: the gather above saw it
+            } else {
+                const float* src = ori_old + 3 * (int64_t)rr;
+                c0 = __ldcg(src); c1 = __ldcg(src + 1); c2 = __ldcg(src + 2);
+            }
             center[3 * i] = c0; center[3 * i + 1] = c1; center[3 * i + 2] = c2;
             const float o0 = ori_old[3 * i], o1 = ori_old[3 * i + 1], o2 = ori_old[3 * i + 2];
             const float nc = fmaxf(mh_norm3(c0, c1, c2), 1e-8f), no = fmaxf(mh_norm3(o0, o1, o2), 1e-8f);
             const float sim = fabsf(((c0 / nc) * (o0 / no) + (c1 / nc) * (o1 / no)) + (c2 / nc) * (o2 / no));   // PMVO.py:631-633
             const bool upd = sim < 0.95f;                                                                      // :634-636
-            ori_new[3 * i] = upd ? c0 : o0; ori_new[3 * i + 1] = upd ? c1 : o1; ori_new[3 * i + 2] = upd ? c2 : o2;
-            sw_red_release(done + c, 1);
+            sw_st(ori_new + 3 * i, upd ? c0 : o0); sw_st(ori_new + 3 * i + 1, upd ? c1 : o1); sw_st(ori_new + 3 * i + 2, upd ? c2 : o2);
         }
         // the next iteration's first barrier (after the ticket draw) orders the reuse of sw_u / s_best
     }
@@ -802,6 +821,7 @@ extern "C" int mh_refine_sweep(void* stream, const float* ori, const int32_t* nb
     const int64_t chunks = (n + sub_num - 1) / sub_num;
     int* ctl = reinterpret_cast<int*>(scratch);
     cudaMemsetAsync(ctl, 0, sizeof(int) * (16 + chunks), st);
+    cudaMemsetAsync(ori_new, 0xff, sizeof(float) * 3 * (size_t)n, st);      // every word PENDING
     const size_t smem = sizeof(float4) * (size_t)K;
     cudaFuncSetAttribute(refine_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;

@@ -14,10 +14,18 @@ from monohair_b200._lib import check, lib, ptr, stream_ptr  # noqa: E402
 
 
 def main():
+    """no argument: BASELINE configs[1] geometry (256 x 256 x 192, 2.5 mm voxels, 1.25 mm candidate cells);
+    `cfg5`: BASELINE configs[4] geometry (512 x 512 x 384, 1.25 mm voxels, 0.625 mm cells: up to 32+ points per voxel)"""
     dev = torch.device("cuda:0")
-    cand = syn.candidate_points(num_per_grid=4, seed=0)
+    big = len(sys.argv) > 1 and sys.argv[1] == "cfg5"
     rng = np.random.default_rng(0)
-    sel = cand[rng.random(cand.shape[0]) < 0.84]
+    if big:
+        cand = syn.candidate_points(num_per_grid=4, seed=0, vsize=0.005 / 8, grid=(1024, 1024, 768))
+        sel = cand[rng.random(cand.shape[0]) < 0.65]
+        P.GRID, P.VOXEL_SIZE = (512, 512, 384), 0.005 / 4
+    else:
+        cand = syn.candidate_points(num_per_grid=4, seed=0)
+        sel = cand[rng.random(cand.shape[0]) < 0.84]
     pts = torch.from_numpy(sel).to(dev).float().contiguous()
     dirs = syn.flow_tangent(pts.double(), syn.RADII).float().contiguous()
     n = pts.size(0)
@@ -55,8 +63,8 @@ def main():
             ref = vol.clone()
         else:
             same = bool(torch.equal(ref, vol))
-        win, cnt = P.voxel_fuse_winners(pts, dirs, dev)
-        vol2 = P.voxel_scatter(win[: int(cnt.item())], dev)
+        win, cnt = P.voxel_fuse_winners(pts, dirs, dev, P.GRID, P.VOXEL_MIN, P.VOXEL_SIZE)
+        vol2 = P.voxel_scatter(win[: int(cnt.item())], dev, P.GRID)
         same = same and bool(torch.equal(vol2, vol))
         print(f"voxel_fuse: n={n} occupied={occ} crowded-max={hdr[1]} winners={hdr[3]} median {ms*1e3:.1f} us min {min(ts)*1e3:.1f} us  "
               f"algorithmic {alg/1e6:.1f} MB -> {alg/ms/1e6:.0f} GB/s = {alg/ms/1e6/6553:.1%} of 6553  plane_clean={clean} same_volume={same}")
