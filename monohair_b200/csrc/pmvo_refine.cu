@@ -795,6 +795,123 @@ refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int
     }
 }
 
+// ---- the same sweep spread over the GPUs of one node -------------------------------------------------------
+// Rank r owns the points of every world-th block of SWD_BLOCK consecutive indices and handles them in increasing order.
+// Every rank keeps a FULL copy of ori_new / center in symmetric memory (each rank can store into every peer's copy over
+// NVLink).  A finished point is stored into ALL copies; a gather that meets the PENDING pattern spins on its OWN copy
+// until the owner's store has landed -- the per-point hand-over of the single-GPU kernel, with the store fanned out over
+// peer memory, so the exchange overlaps the medoid work point by point and no collective follows the kernel.
+// No deadlock: every wait is on a smaller point index, and the globally smallest unfinished point is always the one its
+// owner is working on.  A bounded spin turns a lost peer into an error flag instead of a hung GPU.
+constexpr int SWD_BLOCK = 64;
+constexpr int SWD_MAX_WORLD = 16;
+struct SwdPeers {
+    float* ori_new[SWD_MAX_WORLD];
+    float* center[SWD_MAX_WORLD];
+};
+
+MH_D unsigned swd_ld(const float* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+MH_D void swd_st(float* p, float x) {
+    unsigned v = __float_as_uint(x);
+    if (v == SW_PENDING) v = 0xfffffffeu;
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+MH_D bool swd_wait3(const float* p, float& a, float& b, float& c, long long limit) {
+    unsigned ua = swd_ld(p), ub = swd_ld(p + 1), uc = swd_ld(p + 2);
+    long long spins = 0;
+    while (ua == SW_PENDING || ub == SW_PENDING || uc == SW_PENDING) {
+        if (++spins > limit) return false;
+        __nanosleep(100);
+        ua = swd_ld(p); ub = swd_ld(p + 1); uc = swd_ld(p + 2);
+    }
+    a = __uint_as_float(ua); b = __uint_as_float(ub); c = __uint_as_float(uc);
+    return true;
+}
+
+// ctl: [0] next local ticket, [1] error flag (a wait ran out)
+__global__ void __launch_bounds__(SW_THREADS)
+refine_sweep_dist_kernel(const float* __restrict__ ori_old, SwdPeers peers, const int* __restrict__ nbr_local, int64_t n,
+                         int64_t n_local, int K, int sub_num, int rank, int world, long long spin_limit, int* ctl) {
+    extern __shared__ float4 sw_u[];
+    __shared__ int s_ticket;
+    __shared__ float s_best[SW_THREADS / 32];
+    __shared__ int s_bk[SW_THREADS / 32];
+    __shared__ float s_out[6];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* mine = peers.ori_new[rank];
+    for (;;) {
+        if (tid == 0) s_ticket = atomicAdd(ctl, 1);
+        __syncthreads();
+        const int q = s_ticket;
+        if (q >= n_local) break;
+        const int64_t i = ((int64_t)(q / SWD_BLOCK) * world + rank) * SWD_BLOCK + (q % SWD_BLOCK);
+        const int first = (int)(i / sub_num) * sub_num;
+        bool lost = false;
+        for (int k = tid; k < K; k += SW_THREADS) {
+            const int rr = nbr_local[(int64_t)q * K + k];
+            float a = 0.0f, b = 0.0f, cc = 0.0f;
+            if (rr < first) {
+                lost = !swd_wait3(mine + 3 * (int64_t)rr, a, b, cc, spin_limit) || lost;
+            } else {
+                const float* src = ori_old + 3 * (int64_t)rr;
+                a = __ldcg(src); b = __ldcg(src + 1); cc = __ldcg(src + 2);
+            }
+            const float nn = fmaxf(mh_norm3(a, b, cc), 1e-8f);
+            sw_u[k] = make_float4(a / nn, b / nn, cc / nn, 0.0f);
+        }
+        if (lost) atomicExch(ctl + 1, 1);
+        __syncthreads();
+        float best = -1e30f; int bk = 0x7fffffff;
+        for (int k = tid; k < K; k += SW_THREADS) {
+            const float4 w = sw_u[k];
+            float sm = mh_torch_inner_sum(K, [&](int j) { const float4 v = sw_u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
+            sm = sm / (float)K;
+            if (sm > best) { best = sm; bk = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_bk[warp] = bk; }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 1; w < SW_THREADS / 32; ++w) {
+                const float ob = s_best[w]; const int ok = s_bk[w];
+                if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+            }
+            const int rr = nbr_local[(int64_t)q * K + bk];
+            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+            if (rr < first) {
+                if (!swd_wait3(mine + 3 * (int64_t)rr, c0, c1, c2, spin_limit)) atomicExch(ctl + 1, 1);
+            } else {
+                const float* src = ori_old + 3 * (int64_t)rr;
+                c0 = __ldcg(src); c1 = __ldcg(src + 1); c2 = __ldcg(src + 2);
+            }
+            const float o0 = ori_old[3 * i], o1 = ori_old[3 * i + 1], o2 = ori_old[3 * i + 2];
+            const float nc = fmaxf(mh_norm3(c0, c1, c2), 1e-8f), no = fmaxf(mh_norm3(o0, o1, o2), 1e-8f);
+            const float sim = fabsf(((c0 / nc) * (o0 / no) + (c1 / nc) * (o1 / no)) + (c2 / nc) * (o2 / no));   // PMVO.py:631-633
+            const bool upd = sim < 0.95f;                                                                      // :634-636
+            s_out[0] = upd ? c0 : o0; s_out[1] = upd ? c1 : o1; s_out[2] = upd ? c2 : o2;
+            s_out[3] = c0; s_out[4] = c1; s_out[5] = c2;
+        }
+        __syncthreads();
+        // fan the result out: thread (w, c) stores component c into rank w's copies
+        if (tid < 3 * world) {
+            const int w = tid / 3, c = tid - 3 * w;
+            swd_st(peers.ori_new[w] + 3 * i + c, s_out[c]);
+            peers.center[w][3 * i + c] = s_out[3 + c];
+        }
+        // the next iteration's first barrier orders the reuse of sw_u / s_best / s_out
+    }
+}
+
 __global__ void refine_finish_kernel(const float* __restrict__ upd_loss, const uint8_t* __restrict__ head_filter, int64_t n,
                                      float* __restrict__ loss) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -832,6 +949,60 @@ extern "C" int mh_refine_sweep(void* stream, const float* ori, const int32_t* nb
     refine_sweep_kernel<<<(unsigned)blocks, SW_THREADS, smem, st>>>(ori, ori_new, nbr, n, K, (int)sub_num, center, ctl);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
+    return 0;
+}
+
+
+// Distributed sweep (one node, symmetric memory).  nbr_local: neighbour lists of THIS rank's points in its own order
+// (mh_refine_sweep_dist_index gives the global index of local row q); peer_ori_new / peer_center: `world` device
+// pointers (host array) to every rank's [n][3] copies, peer_*[rank] being the local one.  The caller fills every word of
+// its ori_new copy with 0xffffffff and passes a cross-rank barrier BEFORE the launch, and another one after it (peers
+// keep storing into the local copies until their own kernels end).  error_flag (device int32): set to 1 if a wait ran out.
+extern "C" int64_t mh_refine_sweep_dist_block(void) { return SWD_BLOCK; }
+
+extern "C" int64_t mh_refine_sweep_dist_local_count(int64_t n, int32_t rank, int32_t world) {
+    const int64_t stride = (int64_t)SWD_BLOCK * world;
+    const int64_t full = n / stride, rem = n % stride;
+    int64_t c = full * SWD_BLOCK;
+    const int64_t lo = (int64_t)rank * SWD_BLOCK;
+    if (rem > lo) c += (rem - lo < SWD_BLOCK) ? rem - lo : SWD_BLOCK;
+    return c;
+}
+
+extern "C" int mh_refine_sweep_dist(void* stream, const float* ori, const int32_t* nbr_local, int32_t K, int64_t n,
+                                    int64_t sub_num, int32_t rank, int32_t world, const uint64_t* peer_ori_new,
+                                    const uint64_t* peer_center, double spin_seconds, void* scratch, int64_t scratch_bytes,
+                                    int32_t* error_flag) {
+    MH_CHECK_ARG(ori && peer_ori_new && peer_center && scratch && error_flag, "null pointer");
+    MH_CHECK_ARG(world >= 1 && world <= SWD_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world (<= 16 ranks)");
+    MH_CHECK_ARG(sub_num > 0 && sub_num < (1ll << 30) && K >= 1 && K <= 1024 && n >= 0 && n < (1ll << 31) - 1, "bad arguments");
+    MH_CHECK_ARG(scratch_bytes >= 64, "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_local = mh_refine_sweep_dist_local_count(n, rank, world);
+    cudaMemsetAsync(error_flag, 0, sizeof(int32_t), st);
+    if (n_local == 0) return 0;
+    MH_CHECK_ARG(nbr_local, "null neighbour table");
+    SwdPeers peers;
+    for (int w = 0; w < SWD_MAX_WORLD; ++w) {
+        peers.ori_new[w] = reinterpret_cast<float*>(w < world ? peer_ori_new[w] : 0);
+        peers.center[w] = reinterpret_cast<float*>(w < world ? peer_center[w] : 0);
+        MH_CHECK_ARG(w >= world || (peers.ori_new[w] && peers.center[w]), "null peer buffer");
+    }
+    int* ctl = reinterpret_cast<int*>(scratch);
+    cudaMemsetAsync(ctl, 0, 64, st);
+    const size_t smem = sizeof(float4) * (size_t)K;
+    cudaFuncSetAttribute(refine_sweep_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_sweep_dist_kernel, SW_THREADS, smem);
+    MH_CHECK_ARG(per_sm >= 1, "K too large for the sweep kernel's shared memory");
+    int64_t blocks = (int64_t)mh_sm_count() * per_sm;
+    if (blocks > n_local) blocks = n_local;
+    const long long limit = (long long)((spin_seconds > 0 ? spin_seconds : 2.0) * 4.0e6);      // ~0.25 us per poll
+    refine_sweep_dist_kernel<<<(unsigned)blocks, SW_THREADS, smem, st>>>(ori, peers, nbr_local, n, n_local, K, (int)sub_num,
+                                                                         rank, world, limit, ctl);
+    MH_COUNT_LAUNCH();
+    MH_CHECK_LAUNCH();
+    cudaMemcpyAsync(error_flag, ctl + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
     return 0;
 }
 

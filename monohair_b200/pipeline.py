@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import pmvo as P
-from ._lib import check, lib, ptr, stream_ptr
+from ._lib import MonoHairError, check, lib, ptr, stream_ptr
 
 
 _PINNED = {}               # reusable pinned result buffers of pmvo_job_host (the caller must consume them before the next call)
@@ -33,6 +33,35 @@ def _dist():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist
     return None
+
+
+_SYMM = {}                 # (device index, n) -> (tensor [2, n, 3] in symmetric memory, rendezvous handle)
+
+
+def _sweep_mode(dist, dev):
+    """"peer" (sweep spread over the ranks through symmetric memory, NVLink stores) or "replicated"."""
+    mode = os.environ.get("MH_SWEEP_DIST", "peer")
+    if mode != "peer" or dist is None or dist.get_backend() != "nccl" or torch.device(dev).type != "cuda":
+        return "replicated"
+    return "peer"
+
+
+def _symm_buffers(n, dev, dist):
+    """[2, n, 3] float32 in symmetric memory (row 0 = ori_new, row 1 = center) + the handle carrying every rank's
+    pointer; allocated and exchanged once per size (collective: every rank calls it at the same point)."""
+    import torch.distributed._symmetric_memory as symm_mem
+    key = (torch.device(dev).index, int(n))
+    if key not in _SYMM:
+        t = symm_mem.empty((2, int(n), 3), dtype=torch.float32, device=dev)
+        _SYMM.clear()                                      # one size at a time: a new capture replaces the old buffers
+        _SYMM[key] = (t, symm_mem.rendezvous(t, dist.group.WORLD))
+    return _SYMM[key]
+
+
+def block_cyclic_index(n, rank, world, block, dev):
+    """global indices of the points rank `rank` owns in the distributed sweep, in its processing order."""
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    return idx[(idx // block) % world == rank]
 
 
 def _shard(n, rank, world):
@@ -119,16 +148,39 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
     n = pts.size(0)
     if n == 0:
         return ori.clone(), loss.clone()
-    nbr = knn_stage(pts, pts, k, dev)
     filt = head_filter_stage(pm, pts, pm.visible_threshold).to(torch.uint8).contiguous()
     o_in = ori.contiguous()
-    o_new, center = torch.empty_like(o_in), torch.empty_like(o_in)
-    wsb = lib().mh_refine_sweep_workspace_bytes(n, sub_num)
-    scratch = torch.empty((wsb,), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        check(lib().mh_refine_sweep(stream_ptr(dev), ptr(o_in), ptr(nbr), k, n, sub_num, ptr(o_new), ptr(center),
-                                    ptr(scratch), wsb), "mh_refine_sweep")
     dist = _dist()
+    if _sweep_mode(dist, dev) == "peer":
+        # the sweep spread over the ranks: each rank queries the neighbours of ITS points only (no 400 B/point
+        # all-gather), finished points are stored into every rank's copy over NVLink (mh_refine_sweep_dist)
+        r, w = dist.get_rank(), dist.get_world_size()
+        mine = block_cyclic_index(n, r, w, int(lib().mh_refine_sweep_dist_block()), dev)
+        assert mine.numel() == lib().mh_refine_sweep_dist_local_count(n, r, w)
+        nbr = P.knn(pts, pts[mine].contiguous(), k, dev) if mine.numel() else torch.empty((0, k), dtype=torch.int32, device=dev)
+        buf, hdl = _symm_buffers(n, dev, dist)
+        buf[0].view(torch.int32).fill_(-1)                  # every word PENDING
+        hdl.barrier()                                       # stream-ordered: no peer stores into a copy before its fill
+        po = (C.c_uint64 * w)(*[int(b) for b in hdl.buffer_ptrs])
+        pc = (C.c_uint64 * w)(*[int(b) + 4 * 3 * n for b in hdl.buffer_ptrs])
+        scratch = torch.empty((64,), dtype=torch.uint8, device=dev)
+        err = torch.empty((1,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mh_refine_sweep_dist(stream_ptr(dev), ptr(o_in), ptr(nbr), k, n, sub_num, r, w, po, pc,
+                                             float(os.environ.get("MH_SWEEP_SPIN_S", "2")), ptr(scratch), 64, ptr(err)),
+                  "mh_refine_sweep_dist")
+        hdl.barrier()                                       # peers store into this copy until their kernels end
+        if int(err.item()):
+            raise MonoHairError("distributed sweep: a wait on a peer's result ran out (a rank died or never launched)")
+        o_new, center = buf[0].clone(), buf[1].clone()
+    else:
+        nbr = knn_stage(pts, pts, k, dev)
+        o_new, center = torch.empty_like(o_in), torch.empty_like(o_in)
+        wsb = lib().mh_refine_sweep_workspace_bytes(n, sub_num)
+        scratch = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mh_refine_sweep(stream_ptr(dev), ptr(o_in), ptr(nbr), k, n, sub_num, ptr(o_new), ptr(center),
+                                        ptr(scratch), wsb), "mh_refine_sweep")
     if dist is None:
         upd = pm.refine_loss_raw(pts, center)
     else:

@@ -51,11 +51,24 @@ def main():
         ok &= same
         if dist.get_rank() == 0:
             print(f"{k:12s} identical: {same}")
+    # the chunk-ordered sweep with many small chunks (the job above has one or two): in "peer" mode every rank owns every
+    # world-th block of 64 points and the finished points travel through symmetric memory (mh_refine_sweep_dist)
+    pts, o0, l0 = single["select_p"], single["select_o"], single["min_loss"]
+    for sub in (257, 1000):
+        o_m, l_m = pipeline.refine_stage(pm, pts, o0, l0, sub_num=sub)
+        pipeline._FORCE_SINGLE = True
+        o_s, l_s = pipeline.refine_stage(pm, pts, o0, l0, sub_num=sub)
+        pipeline._FORCE_SINGLE = False
+        same = torch.equal(o_m, o_s) and torch.equal(l_m, l_s)
+        ok &= same
+        if dist.get_rank() == 0:
+            print(f"refine sweep ({pipeline._sweep_mode(dist, dev)}, {pts.size(0)} points, chunks of {sub}) identical: {same}; "
+                  f"{int((o_s != o0).any(1).sum().item())} orientations updated")
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if dist.get_rank() == 0:
         print("MULTI_GPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", "world", dist.get_world_size(),
-              "fusion", os.environ.get("MH_FUSE_DIST", "replicated"),
+              "fusion", os.environ.get("MH_FUSE_DIST", "replicated"), "sweep", os.environ.get("MH_SWEEP_DIST", "peer"),
               "occupied voxels", int(multi["volume"][..., 3].sum().item()))
     dist.destroy_process_group()
     sys.exit(0 if int(t.item()) == 1 else 1)

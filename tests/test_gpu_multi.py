@@ -32,10 +32,10 @@ def _torchrun(script_args, world, env=None, timeout=900):
 
 
 @needs2
-@pytest.mark.parametrize("fusion", ["replicated", "winners"])
-def test_sharded_job_equals_single_gpu_job(fusion):
+@pytest.mark.parametrize("fusion,sweep", [("replicated", "peer"), ("winners", "replicated")])
+def test_sharded_job_equals_single_gpu_job(fusion, sweep):
     world = min(torch.cuda.device_count(), 8)
-    r = _torchrun([os.path.join(ROOT, "tests", "multi_gpu_check.py")], world, env={"MH_FUSE_DIST": fusion})
+    r = _torchrun([os.path.join(ROOT, "tests", "multi_gpu_check.py")], world, env={"MH_FUSE_DIST": fusion, "MH_SWEEP_DIST": sweep})
     assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
