@@ -380,7 +380,7 @@ def run_b200(args, cfg):
             t = torch.tensor([t_e2e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_e2e = float(t.item())
-        d2h = sum(host[k].numel() * host[k].element_size() for k in ("volume", "select_o", "min_loss", "high_conf"))
+        d2h = sum(host[k].numel() * host[k].element_size() for k in ("volume", "select_o", "min_loss", "high_conf") if k in host)   # rank 0 reads back
         e2e = {"value": host["n_optimized"] / t_e2e, "unit": "points/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "s_per_step": t_e2e,
                "api": "PMVO(camera,depths,Ori,Conf,masks) with the reference loaders' float64/float32 arrays (pinned) + "

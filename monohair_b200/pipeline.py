@@ -278,9 +278,11 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None, grid=P.GRID, vox
 
 
 def pmvo_job_host(camera, depths, Ori, Conf, masks, candidates_host, image_size, patch_size, visible_threshold,
-                  conf_threshold, threshold, device="cuda:0", u8=False):
+                  conf_threshold, threshold, device="cuda:0", u8=False, readback=None):
     """End to end from HOST buffers to HOST results: H2D of every view's maps (PMVO.__init__), the job, and the
-    D2H read of the fused volume and per-point results."""
+    D2H read of the fused volume and per-point results.  Several ranks: the results are replicated on every GPU and
+    rank 0 is the one that hands them to the caller / writes the files, so by default only rank 0 reads them back
+    (readback=True forces it everywhere)."""
     if u8:
         pm = P.PMVO.from_u8(camera, depths, Ori, Conf, masks, device=device, image_size=image_size,
                             patch_size=patch_size, visible_threshold=visible_threshold, conf_threshold=conf_threshold)
@@ -290,7 +292,9 @@ def pmvo_job_host(camera, depths, Ori, Conf, masks, candidates_host, image_size,
     cand = torch.as_tensor(candidates_host).to(device, non_blocking=True).type(torch.float).contiguous()
     out = pmvo_job_device(pm, cand, threshold)
     host = {}
-    for k in ("volume", "select_o", "min_loss", "high_conf"):
+    if readback is None:
+        readback = _dist() is None or _dist().get_rank() == 0
+    for k in ("volume", "select_o", "min_loss", "high_conf") if readback else ():
         t = out[k]
         key = (k, tuple(t.shape), t.dtype)
         if key not in _PINNED:
