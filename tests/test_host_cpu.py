@@ -135,3 +135,22 @@ def test_connect_strands_and_chain_following_host_logic():
     # take their partner, but neither side continues back into strand 0
     cyc = np.array([[1, 2, 1, 1], [0, 2, 0, 1]], np.int32)
     assert connect_segments(cyc, [s0, s1], 0).shape[0] == 9
+
+
+@pytest.mark.parametrize("n,world", [(0, 2), (1, 2), (63, 3), (64, 2), (1000, 3), (926011, 8), (5400, 16)])
+def test_distributed_sweep_ownership_partitions_the_points(n, world):
+    """mh_refine_sweep_dist: rank r owns every world-th block of 64 consecutive points, in increasing order; the host
+    index helper and the library's count agree and the ranks' sets partition 0..n-1."""
+    from monohair_b200 import pipeline
+    from monohair_b200._lib import lib
+    L = lib()
+    B = int(L.mh_refine_sweep_dist_block())
+    seen = []
+    for r in range(world):
+        idx = pipeline.block_cyclic_index(n, r, world, B, "cpu")
+        assert idx.numel() == L.mh_refine_sweep_dist_local_count(n, r, world)
+        assert bool((idx[1:] > idx[:-1]).all())
+        q = torch.arange(idx.numel())
+        assert torch.equal(idx, ((q // B) * world + r) * B + q % B)          # the kernel's index formula
+        seen.append(idx)
+    assert torch.equal(torch.sort(torch.cat(seen)).values, torch.arange(n))
