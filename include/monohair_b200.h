@@ -153,12 +153,14 @@ int mh_refine_finish(void* stream, const float* upd_loss, const uint8_t* head_fi
  * local copy; finished points are stored into all copies over NVLink, waits spin on the local copy only, so the exchange
  * overlaps the medoid work and no collective follows the kernel.  The caller fills every word of its ori_new copy with
  * 0xffffffff and passes a cross-rank barrier on the stream BEFORE the call and another one after it.  spin_seconds bounds
- * a wait (<= 0: 2 s); *error_flag (device) is 1 afterwards if one ran out.  Bit-identical to mh_refine_sweep. */
+ * a wait (<= 0: 2 s); *error_flag (device) is 1 afterwards if one ran out; max_blocks > 0 caps the grid (the kernels of all
+ * ranks must be resident together: one per GPU in production, several on one GPU in the tests).  Bit-identical to
+ * mh_refine_sweep. */
 int64_t mh_refine_sweep_dist_block(void);
 int64_t mh_refine_sweep_dist_local_count(int64_t n, int32_t rank, int32_t world);
 int mh_refine_sweep_dist(void* stream, const float* ori, const int32_t* nbr_local, int32_t K, int64_t n, int64_t sub_num,
                          int32_t rank, int32_t world, const uint64_t* peer_ori_new, const uint64_t* peer_center,
-                         double spin_seconds, void* scratch, int64_t scratch_bytes, int32_t* error_flag);
+                         double spin_seconds, int32_t max_blocks, void* scratch, int64_t scratch_bytes, int32_t* error_flag);
 int mh_refine_chunks(void* stream, const mh_views* views, const float* points, const int32_t* nbr, int32_t K,
                      const uint8_t* head_filter, int64_t n, int64_t sub_num, float conf_threshold,
                      float* ori /*in/out*/, float* loss /*out*/, void* scratch, int64_t scratch_bytes);

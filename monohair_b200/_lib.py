@@ -51,7 +51,7 @@ _SIGS = {
     "mh_refine_finish": (C.c_int, [p, p, p, i64, p]),
     "mh_refine_sweep_dist_block": (i64, []),
     "mh_refine_sweep_dist_local_count": (i64, [i64, i32, i32]),
-    "mh_refine_sweep_dist": (C.c_int, [p, p, p, i32, i64, i64, i32, i32, p, p, f64, p, i64, p]),
+    "mh_refine_sweep_dist": (C.c_int, [p, p, p, i32, i64, i64, i32, i32, p, p, f64, i32, p, i64, p]),
     "mh_refine_update": (C.c_int, [p, p, p, p, i64, p, p]),
     "mh_pmvo_optimize_workspace_bytes": (i64, [VP, i64]),
     "mh_pmvo_optimize": (C.c_int, [p, VP, p, i64, p, i32, f32, p, p, p, p, p, p, p, p, p, i64]),

@@ -958,6 +958,7 @@ extern "C" int mh_refine_sweep(void* stream, const float* ori, const int32_t* nb
 // pointers (host array) to every rank's [n][3] copies, peer_*[rank] being the local one.  The caller fills every word of
 // its ori_new copy with 0xffffffff and passes a cross-rank barrier BEFORE the launch, and another one after it (peers
 // keep storing into the local copies until their own kernels end).  error_flag (device int32): set to 1 if a wait ran out.
+// max_blocks > 0 caps the grid (all ranks' kernels must be resident at the same time: one kernel per GPU in production).
 extern "C" int64_t mh_refine_sweep_dist_block(void) { return SWD_BLOCK; }
 
 extern "C" int64_t mh_refine_sweep_dist_local_count(int64_t n, int32_t rank, int32_t world) {
@@ -971,8 +972,8 @@ extern "C" int64_t mh_refine_sweep_dist_local_count(int64_t n, int32_t rank, int
 
 extern "C" int mh_refine_sweep_dist(void* stream, const float* ori, const int32_t* nbr_local, int32_t K, int64_t n,
                                     int64_t sub_num, int32_t rank, int32_t world, const uint64_t* peer_ori_new,
-                                    const uint64_t* peer_center, double spin_seconds, void* scratch, int64_t scratch_bytes,
-                                    int32_t* error_flag) {
+                                    const uint64_t* peer_center, double spin_seconds, int32_t max_blocks, void* scratch,
+                                    int64_t scratch_bytes, int32_t* error_flag) {
     MH_CHECK_ARG(ori && peer_ori_new && peer_center && scratch && error_flag, "null pointer");
     MH_CHECK_ARG(world >= 1 && world <= SWD_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world (<= 16 ranks)");
     MH_CHECK_ARG(sub_num > 0 && sub_num < (1ll << 30) && K >= 1 && K <= 1024 && n >= 0 && n < (1ll << 31) - 1, "bad arguments");
@@ -997,6 +998,7 @@ extern "C" int mh_refine_sweep_dist(void* stream, const float* ori, const int32_
     MH_CHECK_ARG(per_sm >= 1, "K too large for the sweep kernel's shared memory");
     int64_t blocks = (int64_t)mh_sm_count() * per_sm;
     if (blocks > n_local) blocks = n_local;
+    if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;      // tests: several "ranks" co-resident on one GPU
     const long long limit = (long long)((spin_seconds > 0 ? spin_seconds : 2.0) * 4.0e6);      // ~0.25 us per poll
     refine_sweep_dist_kernel<<<(unsigned)blocks, SW_THREADS, smem, st>>>(ori, peers, nbr_local, n, n_local, K, (int)sub_num,
                                                                          rank, world, limit, ctl);

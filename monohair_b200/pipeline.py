@@ -167,7 +167,7 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
         err = torch.empty((1,), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             check(lib().mh_refine_sweep_dist(stream_ptr(dev), ptr(o_in), ptr(nbr), k, n, sub_num, r, w, po, pc,
-                                             float(os.environ.get("MH_SWEEP_SPIN_S", "2")), ptr(scratch), 64, ptr(err)),
+                                             float(os.environ.get("MH_SWEEP_SPIN_S", "2")), 0, ptr(scratch), 64, ptr(err)),
                   "mh_refine_sweep_dist")
         hdl.barrier()                                       # peers store into this copy until their kernels end
         if int(err.item()):

@@ -32,8 +32,10 @@ def build(g, sc):
 
 @pytest.fixture(scope="module", params=CASES)
 def case(request):
+    from monohair_b200 import pmvo as P
     g = load(request.param)
     sc = scene_of(g)
+    P.scalp_tree, P.scalp_max = KDTree(data=g["scalp"]), g["scalp"].max(0)     # module globals of the reference (PMVO.py:99-106)
     return g, sc, build(g, sc)
 
 
@@ -164,6 +166,48 @@ def test_refine_chunks_one_call_equals_staged_pipeline(case):
     # and the sweep really is sequential across chunks: one big chunk (pure Jacobi) gives a different result
     o_j, _ = pipeline.refine_stage(pmvo, pts, ori, loss, sub_num=n, k=k)
     assert not torch.equal(o_j, o_ref)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_distributed_sweep_ranks_simulated_on_one_gpu(case, world):
+    """mh_refine_sweep_dist with `world` ranks played by `world` kernels on separate streams of ONE device (grids capped so
+    that they are resident together), every rank with its own full copy of the output arrays: the cross-rank waits, the
+    fan-out stores and the ownership formula run for real, and every copy must equal mh_refine_sweep's result bit for bit."""
+    import ctypes as C
+    from monohair_b200 import pipeline
+    from monohair_b200 import pmvo as P
+    from monohair_b200._lib import check, lib, ptr
+    g, sc, pmvo = case
+    dev = pmvo.device
+    pts = torch.from_numpy(g["fwd_points"].astype(np.float32)).to(dev).contiguous()
+    ori = torch.from_numpy(g["fwd_ori"].astype(np.float32)).to(dev).contiguous()
+    n, k, sub = pts.size(0), 100, 37
+    L = lib()
+    nbr = P.knn(pts, pts, k, dev)
+    o_ref, c_ref = torch.empty_like(ori), torch.empty_like(ori)
+    wsb = L.mh_refine_sweep_workspace_bytes(n, sub)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    from monohair_b200._lib import stream_ptr
+    check(L.mh_refine_sweep(stream_ptr(dev), ptr(ori), ptr(nbr), k, n, sub, ptr(o_ref), ptr(c_ref), ptr(ws), wsb), "mh_refine_sweep")
+    bufs = [torch.empty((2, n, 3), dtype=torch.float32, device=dev) for _ in range(world)]
+    for b in bufs:
+        b[0].view(torch.int32).fill_(-1)                       # PENDING
+        b[1].zero_()
+    po = (C.c_uint64 * world)(*[b[0].data_ptr() for b in bufs])
+    pc = (C.c_uint64 * world)(*[b[1].data_ptr() for b in bufs])
+    B = int(L.mh_refine_sweep_dist_block())
+    locals_ = [nbr[pipeline.block_cyclic_index(n, r, world, B, dev)].contiguous() for r in range(world)]
+    errs = [torch.zeros((1,), dtype=torch.int32, device=dev) for _ in range(world)]
+    scr = [torch.empty((64,), dtype=torch.uint8, device=dev) for _ in range(world)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    torch.cuda.synchronize()
+    for r in reversed(range(world)):                          # launch the LAST rank first: rank 0's points must still get through
+        check(L.mh_refine_sweep_dist(C.c_void_p(streams[r].cuda_stream), ptr(ori), ptr(locals_[r]), k, n, sub, r, world, po, pc,
+                                     5.0, 48, ptr(scr[r]), 64, ptr(errs[r])), "mh_refine_sweep_dist")
+    torch.cuda.synchronize()
+    assert all(int(e.item()) == 0 for e in errs), "a wait ran out"
+    for b in bufs:
+        assert torch.equal(b[0], o_ref) and torch.equal(b[1], c_ref)
 
 
 def test_voxel_fuse_vs_oracle_exact(case):
