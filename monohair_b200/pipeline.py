@@ -36,6 +36,7 @@ def _dist():
 
 
 _SYMM = {}                 # (device index, n) -> (tensor [2, n, 3] in symmetric memory, rendezvous handle)
+_SYMM_BROKEN = False       # set once if symmetric memory cannot be set up on this box
 
 
 def _sweep_mode(dist, dev):
@@ -48,14 +49,31 @@ def _sweep_mode(dist, dev):
 
 def _symm_buffers(n, dev, dist):
     """[2, n, 3] float32 in symmetric memory (row 0 = ori_new, row 1 = center) + the handle carrying every rank's
-    pointer; allocated and exchanged once per size (collective: every rank calls it at the same point)."""
-    import torch.distributed._symmetric_memory as symm_mem
+    pointer; allocated and exchanged once per size (collective: every rank calls it at the same point).  -> None when
+    symmetric memory cannot be set up on this box (the ranks agree on that through one all-reduce, once), in which case
+    the sweep runs replicated."""
+    global _SYMM_BROKEN
     key = (torch.device(dev).index, int(n))
-    if key not in _SYMM:
+    if key in _SYMM:
+        return _SYMM[key]
+    if _SYMM_BROKEN:
+        return None
+    got = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
         t = symm_mem.empty((2, int(n), 3), dtype=torch.float32, device=dev)
-        _SYMM.clear()                                      # one size at a time: a new capture replaces the old buffers
-        _SYMM[key] = (t, symm_mem.rendezvous(t, dist.group.WORLD))
-    return _SYMM[key]
+        got = (t, symm_mem.rendezvous(t, dist.group.WORLD))
+    except Exception as e:                                  # noqa: BLE001 -- any failure means "no peer access here"
+        import warnings
+        warnings.warn(f"symmetric memory unavailable ({type(e).__name__}: {e}); the medoid sweep runs replicated")
+    ok = torch.tensor([1 if got is not None else 0], device=dev, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        _SYMM_BROKEN = True
+        return None
+    _SYMM.clear()                                           # one size at a time: a new capture replaces the old buffers
+    _SYMM[key] = got
+    return got
 
 
 def block_cyclic_index(n, rank, world, block, dev):
@@ -151,14 +169,15 @@ def refine_stage(pm, pts, ori, loss, sub_num=5000, k=100):
     filt = head_filter_stage(pm, pts, pm.visible_threshold).to(torch.uint8).contiguous()
     o_in = ori.contiguous()
     dist = _dist()
-    if _sweep_mode(dist, dev) == "peer":
+    symm = _symm_buffers(n, dev, dist) if _sweep_mode(dist, dev) == "peer" else None
+    if symm is not None:
         # the sweep spread over the ranks: each rank queries the neighbours of ITS points only (no 400 B/point
         # all-gather), finished points are stored into every rank's copy over NVLink (mh_refine_sweep_dist)
         r, w = dist.get_rank(), dist.get_world_size()
         mine = block_cyclic_index(n, r, w, int(lib().mh_refine_sweep_dist_block()), dev)
         assert mine.numel() == lib().mh_refine_sweep_dist_local_count(n, r, w)
         nbr = P.knn(pts, pts[mine].contiguous(), k, dev) if mine.numel() else torch.empty((0, k), dtype=torch.int32, device=dev)
-        buf, hdl = _symm_buffers(n, dev, dist)
+        buf, hdl = symm
         buf[0].view(torch.int32).fill_(-1)                  # every word PENDING
         hdl.barrier()                                       # stream-ordered: no peer stores into a copy before its fill
         po = (C.c_uint64 * w)(*[int(b) for b in hdl.buffer_ptrs])
