@@ -29,9 +29,10 @@ extern "C" {
 /* Resident per-view maps (PMVO.__init__, PMVO.py:14-37).  All device pointers, owned by the caller. */
 typedef struct mh_views {
     int32_t V, H, W, P;        /* views, image rows, cols, patch size (odd) */
-    const void* mapC;          /* float4 [V][H][W] = {depth, mask', ori_row, ori_col}; mask' = mask>0.2 ? 1 : mask (PMVO.py:427) */
-    const void* mapP;          /* float4 [V][H][W] = {unit_row, unit_col, conf, max_{PxP} conf}: direction pre-normalised
-                                  as torch.cosine_similarity does (PMVO.py:171, 491-515) */
+    const void* mapC;          /* float4 [V][H][W] = {depth, mask', max_{PxP} conf, ori_row}; mask' = mask>0.2 ? 1 : mask
+                                  (PMVO.py:427): all that filter_points reads of a (point, view) pair, in one 32 B sector */
+    const void* mapP;          /* float4 [V][H][W] = {unit_row, unit_col, conf, ori_col}: direction pre-normalised as
+                                  torch.cosine_similarity does (PMVO.py:171, 491-515); raw orientation = (mapC.w, mapP.w) */
     const float* cam;          /* [V][MH_CAM_STRIDE] */
 } mh_views;
 

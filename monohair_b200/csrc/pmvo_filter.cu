@@ -3,8 +3,9 @@
 //   mh_visible_count                     PMVO.compute_unvisible_points (PMVO.py:461-480)
 //   mh_head_count                        PMVO.filter_head_points       (PMVO.py:110-136)
 // One thread per point, views in the outer loop so that all resident CTAs walk the views together and one
-// view's planes (mapC 16 B/px + the .w of mapP) stay L2-resident while they are being gathered.
-// Bound: L2/HBM gather bandwidth; algorithmic bytes per (point, view) = 8 ({depth, mask'} of mapC) + 4 (max conf) = 12 B.
+// view's mapC plane (16 B/px) stays L2-resident while it is being gathered.  Everything these kernels need of a (point, view)
+// pair -- depth, mask', PxP maximum of the confidence -- sits in ONE mapC texel: one 32 B sector per pair.
+// Bound: L2/HBM gather bandwidth; algorithmic bytes per (point, view) = 12 B ({depth, mask', max conf}).
 #include "mh_common.cuh"
 
 namespace {
@@ -26,7 +27,6 @@ count_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, float thr_v,
     MhCascade<NC> acc;
     acc.init(vw.V);
     const float4* __restrict__ mapC = reinterpret_cast<const float4*>(vw.mapC);
-    const float4* __restrict__ mapP = reinterpret_cast<const float4*>(vw.mapP);
     const size_t plane = (size_t)vw.H * vw.W;
     const float Wf = (float)vw.W, Hf = (float)vw.H;
     for (int vb = 0; vb < vw.V; vb += CAM_CHUNK) {
@@ -48,7 +48,7 @@ count_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, float thr_v,
             const float4 dm = __ldg(mapC + pix);
             const float delta = (-cz / 2.0f) * 255.0f - dm.x;
             if (MODE == FILTER) {
-                float cmax = __ldg(reinterpret_cast<const float*>(mapP + pix) + 3);
+                float cmax = dm.z;                                   // PxP maximum, same texel (one sector per pair)
                 if (oob) cmax = 0.0f;
                 const float vis = (delta > 0.1f || oob) ? 0.0f : 1.0f;
                 const float vis1 = (delta > thr_v || oob) ? 0.0f : 1.0f;
@@ -164,7 +164,7 @@ __global__ void centre_kernel(mh_views vw, const float* __restrict__ pts, int64_
     if (oob) vis = -1.0f;
     const size_t o = (size_t)v * N + n;
     visible[o] = vis;
-    ori[2 * o] = dm.z; ori[2 * o + 1] = dm.w;
+    ori[2 * o] = dm.w; ori[2 * o + 1] = oc.w;
     conf[o] = fminf(fmaxf(oc.z, 1e-6f), 1.0f);
     if (mask) mask[o] = dm.y;
     if (rowcol) { rowcol[2 * o] = row; rowcol[2 * o + 1] = oob ? -col - 1 : col; }

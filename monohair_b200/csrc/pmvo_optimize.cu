@@ -247,7 +247,7 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
             const float conf = fminf(fmaxf(oc.z, 1e-6f), 1.0f);
             const float confp = (vis < 1.0f) ? conf * fmaxf(vis, 0.0f) : conf;      // :340
             sm.camz[v] = cz; sm.xp[v] = xp; sm.yp[v] = yp; sm.vis[v] = vis;
-            sm.orr[v] = dm.z; sm.orc[v] = dm.w; sm.pix[v] = pix;
+            sm.orr[v] = dm.w; sm.orc[v] = oc.w; sm.pix[v] = pix;
             sm.q[v].v = confp; sm.q[v].i = v;
         }
         __syncthreads();
@@ -273,7 +273,7 @@ optimize_kernel(mh_views vw, const float* __restrict__ pts, int64_t N, const flo
                 const int pix = sm.pix[v];
                 const int row = pix / vw.W, col = pix - row * vw.W;
                 const float4* __restrict__ mp = mapP + (size_t)v * plane;
-                const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mp + pix) + 3), 1e-6f), 1.0f);
+                const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mapC + (size_t)v * plane + pix) + 2), 1e-6f), 1.0f);
                 const bool hi = cmax > thr_c;                                        // :162
                 float2* sxy = sm.exy + (size_t)v * PP;
                 float* sc = sm.ec + (size_t)v * PP;

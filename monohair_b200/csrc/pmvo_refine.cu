@@ -60,7 +60,7 @@ refine_loss_kernel(mh_views vw, const float* __restrict__ pts, const float* __re
                 mh_cam_to_xy(cm.fx, cm.fy, cm.cx, cm.cy, Wf, Hf, c2x, c2y, c2z, xs, ys);
                 float y0, y1;
                 mh_normalize2(ys - yp, xs - xp, y0, y1);
-                const float cmax = fminf(fmaxf(__ldg(reinterpret_cast<const float*>(mp + (size_t)row * vw.W + col) + 3), 1e-6f), 1.0f);
+                const float cmax = fminf(fmaxf(dm.z, 1e-6f), 1.0f);     // PxP maximum: same texel as depth / mask
                 const bool hi = cmax > thr_c;
                 float bl = 0.0f, bc = 0.0f;
                 for (int di = 0; di < P; ++di) {

@@ -1,9 +1,11 @@
 // Packing of the per-view maps into the two resident planes the PMVO kernels gather from.
-//   mapC float4 {depth, mask', ori_row, ori_col}     one 16 B texel per centre-pixel query (raw orientation: the 2 px
-//                                                    step of sample_next_3d_pos uses it un-normalised, PMVO.py:300)
-//   mapP float4 {unit_row, unit_col, conf, max_PxP conf}   one 16 B texel per patch entry; the direction is stored
+//   mapC float4 {depth, mask', max_PxP conf, ori_row}   everything filter_points needs of a (point, view) pair in ONE
+//                16 B texel = one 32 B sector (the PxP maximum used to sit in mapP: two sectors per pair)
+//   mapP float4 {unit_row, unit_col, conf, ori_col}      one 16 B texel per patch entry; the direction is stored
 //                already normalised the way torch.cosine_similarity normalises it (x / max(||x||, 1e-8)), so the
-//                patch scans do not repeat a sqrt and two divisions per entry
+//                patch scans do not repeat a sqrt and two divisions per entry.  The RAW orientation (ori_row in mapC.w,
+//                ori_col in mapP.w; the 2 px step of sample_next_3d_pos uses it un-normalised, PMVO.py:300) is only read at
+//                the centre pixel, by kernels that fetch both texels there anyway
 // The PxP maximum with edge clamping (get_c_patch + torch.max, PMVO.py:415-418 / :162) equals a max filter
 // over the window intersected with the image, so it is computed once per view here (separable: rows then cols
 // through a shared-memory tile) instead of P*P gathers per (point, view).
@@ -58,10 +60,10 @@ extern "C" int mh_views_pack(void* stream, int32_t v, int32_t H, int32_t W, int3
         float m = __ldg(mask + i * mask_stride);
         m = (m > 0.2f) ? 1.0f : m;                                   // PMVO.py:427 / :124
         const float2 o = __ldg(reinterpret_cast<const float2*>(ori) + i);
-        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, o.x, o.y);
+        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, cmax, o.x);
         float n0, n1;
         mh_normalize2(o.x, o.y, n0, n1);
-        mapP[i] = make_float4(n0, n1, __ldg(conf + i), cmax);
+        mapP[i] = make_float4(n0, n1, __ldg(conf + i), o.y);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
     MH_COUNT_LAUNCH();
@@ -88,10 +90,10 @@ extern "C" int mh_views_pack_f64(void* stream, int32_t v, int32_t H, int32_t W, 
         m = (m > 0.2f) ? 1.0f : m;
         const double2 od = __ldg(reinterpret_cast<const double2*>(ori) + i);
         const float ox = (float)od.x, oy = (float)od.y;
-        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, ox, oy);
+        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, cmax, ox);
         float n0, n1;
         mh_normalize2(ox, oy, n0, n1);
-        mapP[i] = make_float4(n0, n1, (float)__ldg(conf + i), cmax);
+        mapP[i] = make_float4(n0, n1, (float)__ldg(conf + i), oy);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
     MH_COUNT_LAUNCH();
@@ -117,10 +119,10 @@ extern "C" int mh_views_pack_u8(void* stream, int32_t v, int32_t H, int32_t W, i
         m = (m > 0.2f) ? 1.0f : m;
         const int g = __ldg(ori_gray + i);
         const float ox = __ldg(ori_lut + 2 * g), oy = __ldg(ori_lut + 2 * g + 1);
-        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, ox, oy);
+        mapC[i] = make_float4(__ldg(depth + i * depth_stride), m, cmax, ox);
         float n0, n1;
         mh_normalize2(ox, oy, n0, n1);
-        mapP[i] = make_float4(n0, n1, __ldg(conf_lut + __ldg(conf_u8 + i)), cmax);
+        mapP[i] = make_float4(n0, n1, __ldg(conf_lut + __ldg(conf_u8 + i)), oy);
     };
     pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, P / 2, conf_at, emit);
     MH_COUNT_LAUNCH();
