@@ -424,7 +424,7 @@ def knn(ref, query, k, dev):
     ncell = torch.unique(cid[:, 0] * (1 << 40) + cid[:, 1] * (1 << 20) + cid[:, 2]).numel()
     rho = m / max(ncell * h0 ** 3, 1e-30)
     r_k = (3.0 * k / (4.0 * math.pi * rho)) ** (1.0 / 3.0)
-    cell = float(min(max(1.15 * r_k, ext.max() / 1000.0), ext.max()))
+    cell = float(min(max(float(os.environ.get("MH_KNN_CELL_FACTOR", "1.15")) * r_k, ext.max() / 1000.0), ext.max()))   # env: tuning only
     bbox = np.concatenate([lo, hi]).astype(np.float64)
     idx = torch.empty((n, k), dtype=torch.int32, device=dev)
     wsb = lib().mh_knn_workspace_bytes(m, n, k)
