@@ -201,7 +201,8 @@ def run_b200(args, cfg):
     kw = dict(device=dev, image_size=[cfg["H"], cfg["W"]], patch_size=cfg["patch"], visible_threshold=cfg["visible_thr"],
               conf_threshold=cfg["conf_thr"])
     pm = P.PMVO.from_u8(cams, sc.depth, sc.ori_gray, sc.conf_u8, sc.mask_u8, **kw)
-    cand = torch.from_numpy(cand_np).to(dev).float().contiguous()
+    cand64 = torch.from_numpy(cand_np).to(dev).contiguous()        # as loaded (float64): queries of the near-surface kNN
+    cand = cand64.float().contiguous()
     torch.cuda.synchronize()
 
     def barrier():
@@ -222,7 +223,8 @@ def run_b200(args, cfg):
             e = torch.cuda.Event(enable_timing=True)
             e.record(torch.cuda.current_stream(dev))
             evs.append((name, e))
-        out = pipeline.pmvo_job_device(pm, cand, cfg["thr"], stats=stats, mark=mark, grid=grid, voxel_size=voxel_size)
+        out = pipeline.pmvo_job_device(pm, cand, cfg["thr"], stats=stats, mark=mark, grid=grid, voxel_size=voxel_size,
+                                       cand64=cand64 if cand64.dtype == torch.float64 else None)
         if record:
             all_events.append(evs)          # elapsed times are read after the timed region (no extra sync inside it)
         return out

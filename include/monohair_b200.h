@@ -124,6 +124,11 @@ int64_t mh_knn_workspace_bytes(int64_t n_ref, int64_t n_query, int32_t k);
 int mh_knn(void* stream, const float* ref, int64_t n_ref, const float* query, int64_t n_query, int32_t k,
            const double* bbox_host /*{min xyz, max xyz} of ref*/, double cell_size,
            int32_t* idx, void* workspace, int64_t workspace_bytes);
+/* the same with float64 queries (float32 references): PMVO.refine step (iii) queries the KDTree of the selected points with
+ * the float64 candidates of filter_unvisible.npy and casts them to float32 only afterwards (PMVO.py:660-671) */
+int mh_knn_q64(void* stream, const float* ref, int64_t n_ref, const double* query, int64_t n_query, int32_t k,
+           const double* bbox_host /*{min xyz, max xyz} of ref*/, double cell_size,
+           int32_t* idx, void* workspace, int64_t workspace_bytes);
 /* Nearest-reference distance only (k=1), float64 [n_query]: scalp_tree.query(points,k=1) (PMVO.py:104). */
 int mh_nn_dist(void* stream, const double* ref, int64_t n_ref, const float* query, int64_t n_query, double* dist);
 /* medoid of ori[nbr[i][0..K)] under |cos| (compute_points_similarity): out [n][3], out_k int32 [n] (may be NULL). */

@@ -58,6 +58,7 @@ _SIGS = {
     "mh_pmvo_refine_loss": (C.c_int, [p, VP, p, p, i64, f32, p]),
     "mh_knn_workspace_bytes": (i64, [i64, i64, i32]),
     "mh_knn": (C.c_int, [p, p, i64, p, i64, i32, p, f64, p, p, i64]),
+    "mh_knn_q64": (C.c_int, [p, p, i64, p, i64, i32, p, f64, p, p, i64]),
     "mh_nn_dist": (C.c_int, [p, p, i64, p, i64, p]),
     "mh_medoid_gather": (C.c_int, [p, p, p, i64, i32, p, p]),
     "mh_voxel_fuse_workspace_bytes": (i64, [i64, i32, i32, i32]),

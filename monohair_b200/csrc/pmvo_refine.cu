@@ -228,9 +228,10 @@ __device__ void warp_sort256(Cand* buf, int lane) {
     }
 }
 
+template <typename QT>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_query_kernel(Grid g, const float* __restrict__ ref, const int* __restrict__ starts, const int* __restrict__ items,
-                 const float* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx,
+                 const QT* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx,
                  const unsigned char* __restrict__ only_flagged) {
     __shared__ Cand bufs[KNN_WARPS][KNN_BUF];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -332,9 +333,10 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
+template <typename QT>
 __global__ void __launch_bounds__(KF_WARPS * 32)
 knn_query_fast_kernel(Grid g, const float* __restrict__ ref, const int* __restrict__ starts, const int* __restrict__ items,
-                      const float* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx,
+                      const QT* __restrict__ query, int64_t nq, int K, int* __restrict__ out_idx,
                       unsigned char* __restrict__ flags) {
     __shared__ double sd_all[KF_WARPS][KF_CAP];
     __shared__ int si_all[KF_WARPS][KF_CAP];
@@ -584,8 +586,10 @@ extern "C" int64_t mh_knn_workspace_bytes(int64_t n_ref, int64_t n_query, int32_
     return 256 + 4 * (3 * (KNN_MAX_CELLS + 2) + 2 * n_ref + KNN_MAX_CELLS / 4096 + 16) + ((n_query + 15) / 16) * 16;
 }
 
-extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float* query, int64_t n_query, int32_t k,
-                      const double* bbox_host, double cell_size, int32_t* idx, void* workspace, int64_t workspace_bytes) {
+namespace {
+template <typename QT>
+int knn_run(void* stream, const float* ref, int64_t n_ref, const QT* query, int64_t n_query, int32_t k,
+            const double* bbox_host, double cell_size, int32_t* idx, void* workspace, int64_t workspace_bytes) {
     MH_CHECK_ARG(ref && query && idx && workspace && bbox_host, "null pointer");
     MH_CHECK_ARG(k >= 1 && k <= KNN_MAXK && k <= n_ref, "k must be in [1,128] and <= n_ref");
     MH_CHECK_ARG(workspace_bytes >= mh_knn_workspace_bytes(n_ref, n_query, k), "workspace too small");
@@ -621,12 +625,25 @@ extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float
     int64_t blocks = (n_query + KNN_WARPS - 1) / KNN_WARPS;
     const int64_t cap = (int64_t)mh_sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    knn_query_fast_kernel<<<(unsigned)blocks, KF_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx, flags);
+    knn_query_fast_kernel<QT><<<(unsigned)blocks, KF_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx, flags);
     MH_COUNT_LAUNCH();
-    knn_query_kernel<<<(unsigned)blocks, KNN_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx, flags);
+    knn_query_kernel<QT><<<(unsigned)blocks, KNN_WARPS * 32, 0, st>>>(g, ref, starts, items, query, n_query, k, idx, flags);
     MH_COUNT_LAUNCH();
     MH_CHECK_LAUNCH();
     return 0;
+}
+}  // namespace
+
+extern "C" int mh_knn(void* stream, const float* ref, int64_t n_ref, const float* query, int64_t n_query, int32_t k,
+                      const double* bbox_host, double cell_size, int32_t* idx, void* workspace, int64_t workspace_bytes) {
+    return knn_run<float>(stream, ref, n_ref, query, n_query, k, bbox_host, cell_size, idx, workspace, workspace_bytes);
+}
+
+// float64 queries against float32 references: what scipy's KDTree(select_points).query(filter_unvisible_points) sees in
+// PMVO.refine step (iii) (PMVO.py:660-671: the .npy candidates are float64 and are cast to float32 only AFTER the query)
+extern "C" int mh_knn_q64(void* stream, const float* ref, int64_t n_ref, const double* query, int64_t n_query, int32_t k,
+                          const double* bbox_host, double cell_size, int32_t* idx, void* workspace, int64_t workspace_bytes) {
+    return knn_run<double>(stream, ref, n_ref, query, n_query, k, bbox_host, cell_size, idx, workspace, workspace_bytes);
 }
 
 extern "C" int mh_nn_dist(void* stream, const double* ref, int64_t n_ref, const float* query, int64_t n_query, double* dist) {

@@ -251,9 +251,12 @@ def fuse_stage(pm, pts, dirs, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.V
     return P.voxel_scatter(allw, dev, grid)
 
 
-def pmvo_job_device(pm, cand, threshold, stats=None, mark=None, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE):
+def pmvo_job_device(pm, cand, threshold, stats=None, mark=None, grid=P.GRID, voxel_min=P.VOXEL_MIN, voxel_size=P.VOXEL_SIZE,
+                    cand64=None):
     """Whole PMVO job with everything resident on the device.  cand float32 [N,3].  -> dict.
-    `mark(name)` (optional) is called at stage boundaries (bench.py records CUDA events there)."""
+    `mark(name)` (optional) is called at stage boundaries (bench.py records CUDA events there).
+    cand64 (optional): the same candidates as loaded, float64 [N,3] -- the reference queries the near-surface neighbours
+    with the float64 points and casts them to float32 afterwards (PMVO.py:670-671); without it the float32 ones are used."""
     mark = mark or (lambda name: None)
     mark("start")
     surface, filt = filter_stage(pm, cand)
@@ -261,6 +264,7 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None, grid=P.GRID, vox
     n_cov = surface.numel()
     pts = cand[:n_cov][surface].contiguous()
     fu = cand[:n_cov][filt].contiguous()
+    fu_q = cand64[:n_cov][filt].contiguous() if cand64 is not None else fu
     mark("compact")
     ori, loss, hc = forward_stage(pm, pts)
     mark("optimize")
@@ -271,7 +275,7 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None, grid=P.GRID, vox
     dev = pm.device
     if fu.size(0) > 0 and sp.size(0) >= 100:
         fh = head_filter_stage(pm, fu, pm.visible_threshold)
-        center = medoid_stage(so, lambda a, b: P.knn(sp, fu[a:b].contiguous(), 100, dev), fu.size(0), dev)
+        center = medoid_stage(so, lambda a, b: P.knn(sp, fu_q[a:b].contiguous(), 100, dev), fu.size(0), dev)
         # the head-filtered points are masked out of the fusion instead of being compacted away first: the compaction
         # needs a host synchronisation, which would expose the launch latency of the whole fusion
         all_p, all_o = torch.cat([sp, fu], 0), torch.cat([so, center], 0)
@@ -308,8 +312,9 @@ def pmvo_job_host(camera, depths, Ori, Conf, masks, candidates_host, image_size,
     else:
         pm = P.PMVO(camera, depths, Ori, Conf, masks, device=device, image_size=image_size, patch_size=patch_size,
                     visible_threshold=visible_threshold, conf_threshold=conf_threshold)
-    cand = torch.as_tensor(candidates_host).to(device, non_blocking=True).type(torch.float).contiguous()
-    out = pmvo_job_device(pm, cand, threshold)
+    raw = torch.as_tensor(candidates_host).to(device, non_blocking=True).contiguous()
+    cand = raw.type(torch.float).contiguous()
+    out = pmvo_job_device(pm, cand, threshold, cand64=raw if raw.dtype == torch.float64 else None)
     host = {}
     if readback is None:
         readback = _dist() is None or _dist().get_rank() == 0

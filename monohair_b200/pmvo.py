@@ -410,7 +410,7 @@ def optimize(points, pmvo, args, chunk=1 << 20):
 
 
 def knn(ref, query, k, dev):
-    """Exact kNN (float64 distances) of `query` [n,3] among `ref` [m,3], both float32 device tensors."""
+    """Exact kNN (float64 distances) of `query` [n,3] (float32 or float64) among `ref` [m,3] float32, device tensors."""
     m, n = ref.size(0), query.size(0)
     lo_t, hi_t = ref.amin(0), ref.amax(0)
     lo, hi = lo_t.double().cpu().numpy(), hi_t.double().cpu().numpy()
@@ -430,8 +430,9 @@ def knn(ref, query, k, dev):
     wsb = lib().mh_knn_workspace_bytes(m, n, k)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        check(lib().mh_knn(stream_ptr(dev), ptr(ref), m, ptr(query), n, k, bbox.ctypes.data_as(C.c_void_p), cell,
-                           ptr(idx), ptr(ws), wsb), "mh_knn")
+        fn = lib().mh_knn_q64 if query.dtype == torch.float64 else lib().mh_knn
+        check(fn(stream_ptr(dev), ptr(ref), m, ptr(query), n, k, bbox.ctypes.data_as(C.c_void_p), cell,
+                 ptr(idx), ptr(ws), wsb), "mh_knn")
     return idx
 
 
@@ -581,9 +582,11 @@ def refine(points, ori, loss, pmvo, filter_unvisible_points, args, infer_inner=T
     select_points = torch.from_numpy(points[index]).to(dev).type(torch.float).contiguous()
 
     print('compute points orientation near the surface... ')
-    fu = torch.from_numpy(np.ascontiguousarray(filter_unvisible_points)).to(dev).type(torch.float).contiguous()
+    fu_raw = torch.from_numpy(np.ascontiguousarray(filter_unvisible_points)).to(dev).contiguous()
+    fu = fu_raw.type(torch.float).contiguous()
     if fu.size(0) > 0 and select_points.size(0) >= 100:
-        nbr = knn(select_points, fu, 100, dev)
+        # the reference queries the KDTree with the points as loaded (float64) and casts them to float32 afterwards (:670-671)
+        nbr = knn(select_points, fu_raw if fu_raw.dtype == torch.float64 else fu, 100, dev)
         filt = pmvo.filter_head_points(fu, args.PMVO.visible_threshold)
         center = medoid_gather(select_ori, nbr, dev)
         fu_ori = center[~filt]

@@ -280,6 +280,37 @@ def test_knn_exact_vs_kdtree():
     assert np.mean(idx == i_ref) > 0.9999
 
 
+def test_knn_float64_queries_match_kdtree_where_float32_queries_do_not():
+    """PMVO.refine step (iii) queries the KDTree with the float64 candidates and casts them to float32 afterwards
+    (PMVO.py:670-671): mh_knn_q64 must order the neighbours by the float64-query distances.  Queries are placed next to
+    the bisector of two reference points, so that rounding the query to float32 flips the order for some of them."""
+    from monohair_b200 import pmvo as P
+    rng = np.random.default_rng(1)
+    ref = rng.uniform(-0.1, 0.1, (20000, 3)).astype(np.float32)
+    tree = KDTree(data=ref)
+    seeds = rng.uniform(-0.08, 0.08, (3000, 3))
+    _, nn = tree.query(seeds, 100)
+    a, b = ref[nn[:, 98]].astype(np.float64), ref[nn[:, 99]].astype(np.float64)
+    q = 0.5 * (a + b) + rng.normal(0, 1e-9, a.shape)               # float64, ~1e-9 off the bisector of two close-ranked points
+    d64, i64 = tree.query(q, 100)
+    _, i32 = tree.query(q.astype(np.float32), 100)
+    dev = torch.device("cuda:0")
+    refd = torch.from_numpy(ref).to(dev)
+    got64 = P.knn(refd, torch.from_numpy(q).to(dev), 100, dev).cpu().numpy()
+    got32 = P.knn(refd, torch.from_numpy(q.astype(np.float32)).to(dev), 100, dev).cpu().numpy()
+    flips = int((i64 != i32).any(1).sum())
+    print(f"\nfloat32-rounded queries change the neighbour list of {flips} of {len(q)} queries")
+    assert flips > 20                                              # the case exists
+    dd = np.linalg.norm(ref[got64].astype(np.float64) - q[:, None, :], axis=-1)
+    assert np.allclose(dd, d64, rtol=0, atol=1e-13)
+    print(f"entries equal to scipy: float64 queries {np.mean(got64 == i64):.6f}, float32 queries {np.mean(got32 == i32):.6f}; "
+          f"lists equal to the float64 KDTree answer: {np.mean((got64 == i64).all(1)):.4f} (float64 queries) vs "
+          f"{np.mean((got32 == i64).all(1)):.4f} (float32 queries)")
+    assert np.mean(got64 == i64) > 0.9999
+    assert np.mean(got32 == i32) > 0.999          # rounded queries sit within 1e-16 of exact ties: order is implementation-defined
+    assert np.mean((got64 == i64).all(1)) > 0.999 > np.mean((got32 == i64).all(1))
+
+
 def test_knn_fallback_paths():
     """dense clumps (buffer overflow) and hundreds of coincident points (no separating radius) take the general
     kernel; results must still be the exact k nearest by distance."""
