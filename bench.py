@@ -455,6 +455,8 @@ def run_b200(args, cfg):
                         "near_surface": stats["n_fu"],
                         "parallelism": "1 GPU" if world == 1 else
                         f"points sharded over {world} GPUs (filter, forward, kNN, re-score, near-surface medoids); "
+                        f"chunk-ordered medoid sweep {pipeline._sweep_mode(dist, dev)} "
+                        f"({'one kernel per rank storing finished points into every peer copy over NVLink' if pipeline._sweep_mode(dist, dev) == 'peer' and not pipeline._SYMM_BROKEN else 'every rank sweeps all points'}); "
                         f"fusion {os.environ.get('MH_FUSE_DIST', 'replicated')}"},
                 "checksums": checksums,
                 "stage_ms": med, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
