@@ -42,7 +42,8 @@ _SYMM_BROKEN = False       # set once if symmetric memory cannot be set up on th
 def _sweep_mode(dist, dev):
     """"peer" (sweep spread over the ranks through symmetric memory, NVLink stores) or "replicated"."""
     mode = os.environ.get("MH_SWEEP_DIST", "peer")
-    if mode != "peer" or dist is None or dist.get_backend() != "nccl" or torch.device(dev).type != "cuda":
+    if (mode != "peer" or dist is None or dist.get_backend() != "nccl" or torch.device(dev).type != "cuda"
+            or dist.get_world_size() > 16):                  # one node: the kernel takes up to 16 peer pointers
         return "replicated"
     return "peer"
 
