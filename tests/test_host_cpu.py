@@ -154,3 +154,29 @@ def test_distributed_sweep_ownership_partitions_the_points(n, world):
         assert torch.equal(idx, ((q // B) * world + r) * B + q % B)          # the kernel's index formula
         seen.append(idx)
     assert torch.equal(torch.sort(torch.cat(seen)).values, torch.arange(n))
+
+
+def test_symmetric_memory_failure_falls_back_once_and_for_all(monkeypatch):
+    """pipeline._symm_buffers: when symmetric memory cannot be set up the ranks agree on it through one all-reduce, the
+    failure is remembered (no second collective attempt) and the caller gets None -> replicated sweep."""
+    import types
+    import torch.distributed._symmetric_memory as symm_mem
+    from monohair_b200 import pipeline
+    calls = []
+
+    class FakeDist:
+        ReduceOp = types.SimpleNamespace(MIN="min")
+        group = types.SimpleNamespace(WORLD=None)
+
+        def all_reduce(self, t, op=None):
+            calls.append(int(t.item()))
+
+    def boom(*a, **k):
+        raise RuntimeError("no peer access on this box")
+    monkeypatch.setattr(symm_mem, "empty", boom)
+    monkeypatch.setattr(pipeline, "_SYMM", {})
+    monkeypatch.setattr(pipeline, "_SYMM_BROKEN", False)
+    with pytest.warns(UserWarning, match="symmetric memory unavailable"):
+        assert pipeline._symm_buffers(100, "cpu", FakeDist()) is None
+    assert calls == [0] and pipeline._SYMM_BROKEN
+    assert pipeline._symm_buffers(100, "cpu", FakeDist()) is None and calls == [0]
