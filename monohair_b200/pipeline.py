@@ -276,7 +276,7 @@ def pmvo_job_device(pm, cand, threshold, stats=None, mark=None, grid=P.GRID, vox
     dev = pm.device
     if fu.size(0) > 0 and sp.size(0) >= 100:
         fh = head_filter_stage(pm, fu, pm.visible_threshold)
-        center = medoid_stage(so, lambda a, b: P.knn(sp, fu_q[a:b].contiguous(), 100, dev), fu.size(0), dev)
+        center = medoid_stage(so, lambda a, b: P.knn(sp, fu_q[a:b].contiguous(), 100, dev, cell_factor=0.65), fu.size(0), dev)
         # the head-filtered points are masked out of the fusion instead of being compacted away first: the compaction
         # needs a host synchronisation, which would expose the launch latency of the whole fusion
         all_p, all_o = torch.cat([sp, fu], 0), torch.cat([so, center], 0)
