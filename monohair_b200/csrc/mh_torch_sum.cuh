@@ -53,3 +53,27 @@ __device__ __forceinline__ float mh_torch_inner_sum(int K, Get get) {
     for (int l = 0; l < VL; ++l) total += p0[l];
     return total;
 }
+
+// The same sum spread over 8 lanes of a warp (lane l = vl of its group of 8 takes vector lane l of every 8-float vector;
+// the group's lanes then add their partial sums in lane order onto the scalar tail, exactly as above).  Every lane of the
+// group returns the total.  For the last few rows of a K x K medoid matrix: with K = 100, rows 96..99 would otherwise
+// occupy 4 lanes of a warp for a full 100-term row each; 4 groups of 8 lanes finish them in an eighth of the time.
+// Requires K >= 8 and K < 512 (as above); all 32 lanes of the warp must call it (shuffles).
+template <typename Get>
+__device__ __forceinline__ float mh_torch_inner_sum_split8(int K, int lane, Get get) {
+    constexpr int VL = 8;
+    const int vl = lane & 7, gbase = lane & ~7;
+    const int nv = K / VL, rows = nv / 4;
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+    for (int r = 0; r < rows; ++r) p0 += get((4 * r) * VL + vl);
+    for (int i = 4 * rows; i < nv; ++i) p0 += get(i * VL + vl);
+    for (int r = 0; r < rows; ++r) p1 += get((4 * r + 1) * VL + vl);
+    for (int r = 0; r < rows; ++r) p2 += get((4 * r + 2) * VL + vl);
+    for (int r = 0; r < rows; ++r) p3 += get((4 * r + 3) * VL + vl);
+    p0 += p1; p0 += p2; p0 += p3;
+    float total = 0.0f;
+    for (int k = nv * VL; k < K; ++k) total += get(k);
+#pragma unroll
+    for (int l = 0; l < VL; ++l) total += __shfl_sync(0xffffffffu, p0, gbase + l);
+    return total;
+}

@@ -533,11 +533,20 @@ medoid_gather_kernel(const float* __restrict__ ori, const int* __restrict__ nbr,
         }
         __syncwarp();
         float best = -1e30f; int bk = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
+        const int K32 = K & ~31, left = K - K32;
+        const bool split = left >= 1 && left <= 4 && K >= 8;            // the last rows: 8 lanes each (mh_torch_sum.cuh)
+        for (int k = lane; k < (split ? K32 : K); k += 32) {
             const float4 w = u[k];
             float s = mh_torch_inner_sum(K, [&](int j) { const float4 v = u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
             s = s / (float)K;
             if (s > best) { best = s; bk = k; }        // ascending k: first maximum kept
+        }
+        if (split) {
+            const int k = min(K32 + (lane >> 3), K - 1);
+            const float4 w = u[k];
+            float s = mh_torch_inner_sum_split8(K, lane, [&](int j) { const float4 v = u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
+            s = s / (float)K;
+            if ((lane >> 3) < left && s > best) { best = s; bk = k; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -773,11 +782,20 @@ refine_sweep_kernel(const float* __restrict__ ori_old, float* ori_new, const int
         }
         __syncthreads();
         float best = -1e30f; int bk = 0x7fffffff;
-        for (int k = tid; k < K; k += SW_THREADS) {
+        const int K32 = K & ~31, left = K - K32;
+        const bool split = left >= 1 && left <= 4 && K >= 8;            // the last rows: 8 lanes each (mh_torch_sum.cuh)
+        for (int k = tid; k < (split ? K32 : K); k += SW_THREADS) {
             const float4 w = sw_u[k];
             float sm = mh_torch_inner_sum(K, [&](int j) { const float4 v = sw_u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
             sm = sm / (float)K;
             if (sm > best) { best = sm; bk = k; }        // ascending k: first maximum kept
+        }
+        if (split && warp == (K32 >> 5) % (SW_THREADS / 32)) {          // the warp that would have had those rows
+            const int k = min(K32 + (lane >> 3), K - 1);
+            const float4 w = sw_u[k];
+            float sm = mh_torch_inner_sum_split8(K, lane, [&](int j) { const float4 v = sw_u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
+            sm = sm / (float)K;
+            if ((lane >> 3) < left && sm > best) { best = sm; bk = k; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -883,11 +901,20 @@ refine_sweep_dist_kernel(const float* __restrict__ ori_old, SwdPeers peers, cons
         if (lost) atomicExch(ctl + 1, 1);
         __syncthreads();
         float best = -1e30f; int bk = 0x7fffffff;
-        for (int k = tid; k < K; k += SW_THREADS) {
+        const int K32 = K & ~31, left = K - K32;
+        const bool split = left >= 1 && left <= 4 && K >= 8;            // the last rows: 8 lanes each (mh_torch_sum.cuh)
+        for (int k = tid; k < (split ? K32 : K); k += SW_THREADS) {
             const float4 w = sw_u[k];
             float sm = mh_torch_inner_sum(K, [&](int j) { const float4 v = sw_u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
             sm = sm / (float)K;
             if (sm > best) { best = sm; bk = k; }
+        }
+        if (split && warp == (K32 >> 5) % (SW_THREADS / 32)) {          // the warp that would have had those rows
+            const int k = min(K32 + (lane >> 3), K - 1);
+            const float4 w = sw_u[k];
+            float sm = mh_torch_inner_sum_split8(K, lane, [&](int j) { const float4 v = sw_u[j]; return fabsf((w.x * v.x + w.y * v.y) + w.z * v.z); });
+            sm = sm / (float)K;
+            if ((lane >> 3) < left && sm > best) { best = sm; bk = k; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
