@@ -185,12 +185,12 @@ def test_symmetric_memory_failure_falls_back_once_and_for_all(monkeypatch):
 def test_product_never_reaches_for_the_oracle_or_a_cpu_fallback():
     """oracle/ is test infrastructure: nothing the product ships may import it, and the library loader has no fallback."""
     import glob
-    shipped = glob.glob(os.path.join(ROOT, "monohair_b200", "**", "*.py"), recursive=True) + \\
-        [os.path.join(ROOT, f) for f in ("PMVO.py", "HairGrow.py", "options.py")] + \\
+    shipped = glob.glob(os.path.join(ROOT, "monohair_b200", "**", "*.py"), recursive=True) + \
+        [os.path.join(ROOT, f) for f in ("PMVO.py", "HairGrow.py", "options.py")] + \
         glob.glob(os.path.join(ROOT, "Utils", "*.py")) + glob.glob(os.path.join(ROOT, "preprocess_capture_data", "*.py"))
     assert len(shipped) > 10
     for f in shipped:
         src = open(f).read()
-        assert not re.search(r"^\\s*(from|import)\\s+oracle\\b", src, re.M), f"{f} imports oracle/"
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle/"
     loader = open(os.path.join(ROOT, "monohair_b200", "_lib.py")).read()
     assert "no CPU fallback" in loader and "raise MonoHairError" in loader
